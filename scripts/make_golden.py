@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own importable functions.
+
+Run in the build container only (needs /root/reference):  python scripts/make_golden.py
+The fixtures travel to the GPU box; /root/reference does not.
+
+Reference functions executed (unmodified, imported from /root/reference):
+  calculate_metrics.calculate_metrics            calculate_metrics.py:17-55
+  eval.evaluation.compute_errors                 eval/evaluation.py:16-60
+  eval.evaluation.compose_poses (+quaternion_*)  eval/evaluation.py:279-485
+  scipy Rotation.from_quat(..).as_matrix()       as used by depth_to_pointcloud.py:168
+and the explicit back-projection block of depth_to_pointcloud_dav2.py:300-313 (inline code in
+``main``; not importable as a function, so its six numpy lines are evaluated here on the fixture).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def synth_depth_pair(rng, H, W, invalid_frac=0.02):
+    gt = np.clip(rng.gamma(2.0, 0.15, size=(H, W)), 0, 1).astype(np.float32)
+    gt[rng.random((H, W)) < invalid_frac] = 0.0
+    pred = (np.where(gt > 0, gt, 0.3) * rng.normal(1.0, 0.07, size=(H, W))).astype(np.float32)
+    return gt, pred
+
+
+def main():
+    sys.path.insert(0, REF)
+    import calculate_metrics as ref_cm  # noqa: E402
+    from eval import evaluation as ref_ev  # noqa: E402
+    from scipy.spatial.transform import Rotation as R  # noqa: E402
+
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # ---- metrics: per-frame calculate_metrics and per-batch compute_errors -----------------
+    B, H, W = 3, 70, 98
+    gts, preds, cm_rows, = [], [], []
+    for _ in range(B):
+        gt, pred = synth_depth_pair(rng, H, W)
+        pred[rng.random((H, W)) < 0.01] = 0.0  # exercises the pred>0 guard / division by zero
+        gts.append(gt)
+        preds.append(pred)
+        m = ref_cm.calculate_metrics(gt.copy(), pred.copy())
+        cm_rows.append([m[k] for k in ("rmse", "mae", "abs_rel", "sq_rel", "delta1", "delta2", "delta3")])
+    gt_b, pred_b = np.stack(gts), np.stack(preds)
+    # lightning_model.py:304-313 : batch-wide mask then compute_errors
+    tg, tp = torch.from_numpy(gt_b)[:, None], torch.from_numpy(pred_b)[:, None]
+    mask = (tg >= 1e-6) & (tg <= 20.0)
+    ce = ref_ev.compute_errors(tp[mask].flatten(), tg[mask].flatten())
+    # SURVEY 8c spot case (seed 0, 518^2)
+    r0 = np.random.default_rng(0)
+    gt0 = np.clip(r0.gamma(2.0, 0.03, size=(518, 518)), 0, 0.2).astype(np.float32)
+    pred0 = (gt0 * r0.normal(1.0, 0.05, size=(518, 518))).astype(np.float32)
+    m0 = ref_cm.calculate_metrics(gt0.copy(), pred0.copy())
+    t0g, t0p = torch.from_numpy(gt0), torch.from_numpy(pred0)
+    mk = (t0g >= 1e-6) & (t0g <= 20.0)
+    c0 = ref_ev.compute_errors(t0p[mk].flatten(), t0g[mk].flatten())
+    empty = ref_cm.calculate_metrics(np.zeros((4, 4), np.float32), np.ones((4, 4), np.float32))
+    np.savez_compressed(
+        os.path.join(OUT, "metrics_small.npz"),
+        gt=gt_b, pred=pred_b,
+        calculate_metrics=np.asarray(cm_rows, dtype=np.float64),
+        compute_errors=np.asarray([float(ce[k]) for k in ("d1", "abs_rel", "rmse", "l1")], dtype=np.float64),
+        spot518_calculate_metrics=np.asarray([m0[k] for k in ("rmse", "mae", "abs_rel", "sq_rel", "delta1", "delta2", "delta3")], dtype=np.float64),
+        spot518_compute_errors=np.asarray([float(c0[k]) for k in ("d1", "abs_rel", "rmse", "l1")], dtype=np.float64),
+        empty_is_nan=np.asarray([np.isnan(v) for v in empty.values()]),
+    )
+
+    # ---- pose chain ---------------------------------------------------------------------
+    N = 64
+    t = rng.normal(0, 0.01, size=(N, 3)).astype(np.float32)
+    rv = np.deg2rad(rng.normal(0, 2.0, size=(N, 3)))
+    q = R.from_rotvec(rv).as_quat().astype(np.float32)  # xyzw
+    rel = np.concatenate([t, q], axis=1).astype(np.float32)
+    rel[17, 3:] = 0.0  # zero quaternion -> identity branch (eval/evaluation.py:331-338)
+    rel[30, 3:] *= 1.3  # non-unit quaternion: the reference does not normalise
+    absp = ref_ev.compose_poses(torch.from_numpy(rel)).numpy()
+    init = np.array([0.1, -0.2, 0.3, *R.from_rotvec([0.1, 0.2, -0.3]).as_quat()], dtype=np.float32)
+    absp_init = ref_ev.compose_poses(torch.from_numpy(rel), torch.from_numpy(init)).numpy()
+    mats = np.stack([R.from_quat(p[3:].astype(np.float64)).as_matrix() for p in absp_init])
+    np.savez_compressed(os.path.join(OUT, "poses_small.npz"), rel=rel, abs=absp, init=init, abs_init=absp_init, rot=mats)
+
+    # ---- explicit back-projection block (depth_to_pointcloud_dav2.py:300-313) -------------
+    H, W = 37, 53
+    z = np.clip(rng.gamma(2.0, 0.03, size=(H, W)), 0, 0.2).astype(np.float32)
+    fx, fy, cx, cy = 156.0418 * W / 475, 155.7529 * H / 475, 178.5604 * W / 475, 181.8043 * H / 475
+    x, y = np.meshgrid(np.arange(W), np.arange(H))
+    x = (x - cx) / fx
+    y = (y - cy) / fy
+    points = np.stack((np.multiply(x, z), np.multiply(y, z), z), axis=-1).reshape(-1, 3)
+    T = np.eye(4)
+    T[:3, :3] = R.from_quat(absp_init[5, 3:].astype(np.float64)).as_matrix()  # depth_to_pointcloud.py:168-173
+    T[:3, 3] = absp_init[5, :3]
+    world = points @ T[:3, :3].T + T[:3, 3]
+    np.savez_compressed(os.path.join(OUT, "backproject_small.npz"), depth=z, k4=np.array([fx, fy, cx, cy]), points=points, T=T, world=world)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
