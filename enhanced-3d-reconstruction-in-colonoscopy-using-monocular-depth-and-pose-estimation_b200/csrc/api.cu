@@ -1,0 +1,156 @@
+// extern "C" surface of libdav2_b200.so (declared in include/dav2_b200.h).
+#include <new>
+
+#include "engine.cuh"
+
+using namespace dav2;
+
+struct dav2_model {
+  Model impl;
+  explicit dav2_model(const dav2_config& c) : impl(c) {}
+};
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int require_sm100() {
+  int dev = 0;
+  DAV2_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0;
+  DAV2_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DAV2_CHECK(major == 10, "dav2_b200 needs an sm_100 (B200) device; found compute capability major %d. There is no fallback path.", major);
+  return 0;
+}
+
+extern "C" {
+
+int dav2_create(dav2_model** out, const dav2_config* cfg) {
+  DAV2_CHECK(out && cfg, "dav2_create: null argument");
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(cfg->embed_dim % 128 == 0 && cfg->embed_dim <= 1024 && cfg->embed_dim == cfg->num_heads * 64,
+             "dav2_create: embed_dim=%d heads=%d unsupported (need D = 64*heads, multiple of 128, <= 1024)",
+             cfg->embed_dim, cfg->num_heads);
+  DAV2_CHECK(cfg->features % 16 == 0 && cfg->depth > 0, "dav2_create: features=%d depth=%d unsupported", cfg->features, cfg->depth);
+  for (int i = 0; i < 4; ++i)
+    DAV2_CHECK(cfg->out_channels[i] % 8 == 0 && cfg->tap_layers[i] >= 0 && cfg->tap_layers[i] < cfg->depth,
+               "dav2_create: out_channels / tap_layers entry %d invalid", i);
+  dav2_model* m = new (std::nothrow) dav2_model(*cfg);
+  DAV2_CHECK(m != nullptr, "dav2_create: out of host memory");
+  *out = m;
+  return 0;
+}
+
+void dav2_destroy(dav2_model* m) { delete m; }
+
+int dav2_set_weight(dav2_model* m, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+  DAV2_CHECK(m, "null model");
+  return m->impl.set_weight(key, data, shape, ndim);
+}
+
+int dav2_weights_complete(const dav2_model* m) {
+  if (!m) return 0;
+  std::string missing;
+  const bool ok = m->impl.weights_complete(&missing);
+  if (!ok) set_last_error("missing weight: %s", missing.c_str());
+  return ok ? 1 : 0;
+}
+
+int dav2_set_pos_embed(dav2_model* m, int32_t ph, int32_t pw, const float* table) {
+  DAV2_CHECK(m, "null model");
+  return m->impl.set_pos_embed(ph, pw, table);
+}
+
+int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W, float* depth, void* stream) {
+  DAV2_CHECK(m, "null model");
+  return m->impl.forward(x, B, H, W, depth, S(stream));
+}
+
+int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* bytes) {
+  DAV2_CHECK(m && name && ptr && bytes, "dav2_debug_buffer: null argument");
+  return m->impl.debug_buffer(name, ptr, bytes);
+}
+
+int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float* out, int32_t Ho, int32_t Wo,
+                      void* stream) {
+  DAV2_CHECK(in && out, "dav2_resize_depth: null pointer");
+  if (int rc = require_sm100()) return rc;
+  return launch_bilinear_f32(in, out, B, Hi, Wi, Ho, Wo, S(stream));
+}
+
+int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
+                     const double* T12, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
+                     int32_t* counts, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_backproject(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, xyz, valid, counts, S(stream));
+}
+
+int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float lo, float hi,
+                       int32_t variant, int32_t per_frame, double* partials, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_depth_metrics(pred, gt, B, HW, lo, hi, variant, per_frame, partials, S(stream));
+}
+
+int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* abs7, double* T12, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_compose_poses(rel, init7, N, abs7, T12, S(stream));
+}
+
+int dav2_linear_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                     int32_t act, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(A && W && C && K % 8 == 0, "dav2_linear_bf16: null pointer or K %% 8 != 0");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = C; p.ldo = N; p.bias = bias; p.act = act;
+  return gemm_linear(GM_LINEAR_BF16, (const bf16*)A, M, K, K, (const bf16*)W, N, p, S(stream));
+}
+
+int dav2_linear_resid(const void* A, const void* W, const float* bias, const float* gamma, float* x, int32_t M,
+                      int32_t N, int32_t K, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(A && W && x && gamma && K % 8 == 0, "dav2_linear_resid: null pointer or K %% 8 != 0");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = x; p.ldo = N; p.bias = bias; p.gamma = gamma;
+  return gemm_linear(GM_LINEAR_RESID, (const bf16*)A, M, K, K, (const bf16*)W, N, p, S(stream));
+}
+
+int dav2_conv3x3_bf16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
+                      void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                      int32_t act, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(in && Wp && out, "dav2_conv3x3_bf16: null pointer");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = out; p.out_relu = (bf16*)out_relu; p.bias = bias; p.add1 = (const bf16*)add1; p.add2 = (const bf16*)add2;
+  p.act = act;
+  return conv3x3(GM_CONV_BF16, (const bf16*)in, B, H, W, Cin, (const bf16*)Wp, Cout, p, S(stream));
+}
+
+int dav2_attention_bf16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(qkv && out, "dav2_attention_bf16: null pointer");
+  uint32_t lbo = 1024, sbo = 1024;
+  if (const char* e = getenv("DAV2_ATT_VLBO")) lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("DAV2_ATT_VSBO")) sbo = (uint32_t)atoi(e);
+  return launch_attention((const bf16*)qkv, (bf16*)out, B, N, D, S(stream), lbo, sbo);
+}
+
+int dav2_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t D, float eps,
+                   void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(x && w && b && out, "dav2_layernorm: null pointer");
+  return launch_layernorm(x, w, b, (bf16*)out, rows, D, 1, 0, eps, S(stream));
+}
+
+int dav2_bilinear_nhwc_bf16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                            int32_t C, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(in && out, "dav2_bilinear_nhwc_bf16: null pointer");
+  return launch_bilinear_nhwc((const bf16*)in, (bf16*)out, B, Hi, Wi, Ho, Wo, C, S(stream));
+}
+
+const char* dav2_last_error(void) { return get_last_error(); }
+int64_t dav2_launch_count(void) { return launch_count(); }
+const char* dav2_version(void) { return "dav2_b200 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
+
+}  // extern "C"

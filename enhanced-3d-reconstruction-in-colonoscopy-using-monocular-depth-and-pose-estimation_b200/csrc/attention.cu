@@ -1,0 +1,259 @@
+// Fused flash-style attention for DINOv2 (d_head = 64, non-causal, arbitrary token count) on sm_100a.
+//
+// One CTA = one 128-query tile of one (image, head); 2 CTAs co-reside per SM so that one CTA's
+// softmax (MUFU-bound) overlaps the other's tensor-core work.
+//   warp 0 (1 lane) : TMA producer  - Q once, then K/V tiles through a 2-deep smem ring
+//   warp 1 (1 lane) : MMA issuer    - S = Q K^T (tcgen05, 128x128x64 -> TMEM cols [0,128)),
+//                                     O_part = P V (128x64x128 -> TMEM cols [128,192)), V is the
+//                                     MN-major B operand straight from the [token, 3D] qkv buffer
+//   warps 2..5      : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
+//                                     fp32, P -> bf16 into 128B-swizzled smem (A operand of the PV MMA),
+//                                     running O kept in registers (o = o*alpha + O_part)
+// Q was pre-scaled by d^-1/2 = 0.125 (folded exactly into the qkv weights), so S needs no scale.
+// Reads qkv bf16 [B*N, 3*D] (q | k | v, head h at columns h*64), writes out bf16 [B*N, D].
+#include "common.cuh"
+
+namespace dav2 {
+
+struct AttnParams {
+  bf16* out;
+  int N;      // tokens per image
+  int D;      // model width (= heads * 64)
+  int nkv;    // ceil(N / 128)
+  uint32_t v_lbo, v_sbo;  // MN-major descriptor strides for V (bytes)
+};
+
+static constexpr int ATT_TILE = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
+static constexpr int ATT_SMEM = 7 * ATT_TILE + 128;  // Q, K0, K1, V0, V1, P(2 tiles), barriers
+static constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(192, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) __trap();  // swizzle-128B tiles need 1024 B alignment
+  const uint32_t sQ = base;
+  const uint32_t sK = base + ATT_TILE;       // 2 stages
+  const uint32_t sV = base + 3 * ATT_TILE;   // 2 stages
+  const uint32_t sP = base + 5 * ATT_TILE;   // 2 swizzle atoms (keys 0-63, 64-127)
+  const uint32_t bars = base + 7 * ATT_TILE;
+  const uint32_t BAR_Q = bars, BAR_KV_FULL = bars + 8, BAR_KV_EMPTY = bars + 24, BAR_S_FULL = bars + 40,
+                 BAR_S_EMPTY = bars + 48, BAR_P_FULL = bars + 56, BAR_O_FULL = bars + 64;
+  const uint32_t tmem_slot = bars + 72;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 7 * ATT_TILE + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * p.N;            // first token row of this image in the [B*N, 3D] buffer
+  const int q0 = qt * 128;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(BAR_Q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR_KV_FULL + 8 * s, 1);
+      mbar_init(BAR_KV_EMPTY + 8 * s, 1);
+    }
+    mbar_init(BAR_S_FULL, 1);
+    mbar_init(BAR_S_EMPTY, 128);
+    mbar_init(BAR_P_FULL, 128);
+    mbar_init(BAR_O_FULL, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (threadIdx.x == 0) {
+    // ---------------- TMA producer ----------------
+    mbar_expect_tx(BAR_Q, ATT_TILE);
+    tma_load_2d(sQ, &tmQKV, BAR_Q, h * 64, row0 + q0);
+    for (int j = 0; j < p.nkv; ++j) {
+      const int s = j & 1;
+      mbar_wait(BAR_KV_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      mbar_expect_tx(BAR_KV_FULL + 8 * s, 2 * ATT_TILE);
+      tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
+      tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
+    }
+  } else if (threadIdx.x == 32) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V   : V is MN-major
+    const uint64_t qdesc = make_sw128_desc(sQ, 16, 1024);
+    mbar_wait(BAR_Q, 0);
+    mbar_wait(BAR_KV_FULL, 0);
+    tc_fence_after();
+    {
+      const uint64_t kdesc = make_sw128_desc(sK, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
+      umma_commit(BAR_S_FULL);
+    }
+    for (int j = 0; j < p.nkv; ++j) {
+      const int s = j & 1;
+      if (j + 1 < p.nkv) {
+        const int s1 = (j + 1) & 1;
+        mbar_wait(BAR_KV_FULL + 8 * s1, (uint32_t)((j + 1) >> 1) & 1u);
+        mbar_wait(BAR_S_EMPTY, (uint32_t)j & 1u);  // softmax finished reading S(j)
+        tc_fence_after();
+        const uint64_t kdesc = make_sw128_desc(sK + s1 * ATT_TILE, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
+        umma_commit(BAR_S_FULL);
+      }
+      mbar_wait(BAR_P_FULL, (uint32_t)j & 1u);  // P(j) in smem, O_part(j-1) consumed
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
+        const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
+        umma_bf16(tO, pdesc, vdesc, idesc_o, (uint32_t)(k != 0));
+      }
+      umma_commit(BAR_O_FULL);
+      umma_commit(BAR_KV_EMPTY + 8 * s);
+    }
+  } else if (warp >= 2) {
+    // ---------------- softmax / output (one query row per thread) ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row within the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, a_prev = 0.f;
+    uint32_t v[32];
+
+    for (int j = 0; j < p.nkv; ++j) {
+      const int nvalid = p.N - j * 128;  // keys of this tile inside the image (>= 1)
+      mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (nvalid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = mx;
+      const float a = fast_exp2((m - m_new) * LOG2E);  // m = -inf on the first tile -> 0
+      const float mscaled = m_new * LOG2E;
+      if (j > 0) {
+        // fold O_part(j-1) into the running output; it also frees the P buffer for P(j)
+        mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tO + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], a_prev, __uint_as_float(v[i]));
+        }
+      }
+      // pass 2: P = exp2(S*log2e - m*log2e) -> bf16 -> swizzled smem
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
+          float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
+          if (c * 32 + 2 * i >= nvalid) e0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= nvalid) e1 = 0.f;
+          rowsum += e0 + e1;
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+        const uint32_t rowbase = sP + (uint32_t)(c >> 1) * ATT_TILE + (uint32_t)r * 128u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t chunk = (uint32_t)((c & 1) * 4 + g) ^ ((uint32_t)r & 7u);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(pk[4 * g]),
+                       "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR_S_EMPTY);  // S(j) fully read: the issuer may overwrite it with S(j+1)
+      fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(BAR_P_FULL);
+      l = fmaf(l, a, rowsum);
+      m = m_new;
+      a_prev = a;
+    }
+    // last partial product
+    mbar_wait(BAR_O_FULL, (uint32_t)(p.nkv - 1) & 1u);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(tO + lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], a_prev, __uint_as_float(v[i]));
+    }
+    if (q0 + r < p.N) {
+      const float inv = 1.0f / l;
+      bf16* dst = p.out + (long long)(row0 + q0 + r) * p.D + h * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(o[8 * g] * inv, o[8 * g + 1] * inv);
+        u.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+        u.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
+        u.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + 8 * g) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_attention(const bf16* qkv, bf16* out, int B, int N, int D, cudaStream_t stream, uint32_t v_lbo,
+                     uint32_t v_sbo) {
+  DAV2_CHECK(D % 64 == 0 && N > 0 && B > 0, "attention: bad shape B=%d N=%d D=%d", B, N, D);
+  CUtensorMap tm;
+  if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  AttnParams p;
+  p.out = out;
+  p.N = N;
+  p.D = D;
+  p.nkv = (N + 127) / 128;
+  p.v_lbo = v_lbo;
+  p.v_sbo = v_sbo;
+  dim3 grid((N + 127) / 128, D / 64, B);
+  attention_kernel<<<grid, 192, ATT_SMEM, stream>>>(tm, p);
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace dav2

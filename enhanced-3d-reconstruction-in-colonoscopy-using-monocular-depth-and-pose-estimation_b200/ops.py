@@ -1,0 +1,159 @@
+"""Operator-level host wrappers over the C ABI (torch tensors in, torch tensors out).
+
+torch is used for device memory and streams only; every computation below is a hand-written
+sm_100a kernel inside libdav2_b200.so.  All tensors must live on the GPU."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream_ptr, require_cuda
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0) -> torch.Tensor:
+    """act(a[M,K] @ w[N,K]^T + bias) -> bf16 [M,N]   (act: 0 none, 1 GELU(erf), 2 ReLU)."""
+    require_cuda(a, "a"); require_cuda(w, "w")
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    check(_lib.load().dav2_linear_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, act,
+                                       current_stream_ptr(a.device)), "dav2_linear_bf16")
+    return out
+
+
+def linear_resid_(x: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """x[M,N] (fp32, in place) += gamma * (a @ w^T + bias)."""
+    require_cuda(x, "x"); require_cuda(a, "a"); require_cuda(w, "w")
+    assert x.dtype == torch.float32 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.shape == (M, N)
+    check(_lib.load().dav2_linear_resid(a.data_ptr(), w.data_ptr(), _ptr(bias), gamma.data_ptr(), x.data_ptr(), M, N, K,
+                                        current_stream_ptr(a.device)), "dav2_linear_resid")
+    return x
+
+
+def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [Cout,Cin,3,3] (any float dtype) -> bf16 [Cout, 9*Cpad], tap-major, Cpad=ceil64(Cin)."""
+    Cout, Cin = w.shape[:2]
+    Cpad = (Cin + 63) // 64 * 64
+    p = torch.zeros(Cout, 9, Cpad, dtype=torch.bfloat16, device=w.device)
+    p[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    return p.reshape(Cout, 9 * Cpad).contiguous()
+
+
+def conv3x3_bf16(x, wp, bias=None, add1=None, add2=None, act: int = 0, want_relu: bool = False):
+    """3x3/pad1 conv on NHWC bf16: x [B,H,W,Cin], wp from pack_conv3x3_weight -> out [B,H,W,Cout] (, relu(out))."""
+    require_cuda(x, "x"); require_cuda(wp, "wp")
+    B, H, W, Cin = x.shape
+    Cout = wp.shape[0]
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x.device)
+    out_relu = torch.empty_like(out) if want_relu else None
+    check(_lib.load().dav2_conv3x3_bf16(x.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(add1), _ptr(add2), out.data_ptr(),
+                                        _ptr(out_relu), B, H, W, Cin, Cout, act, current_stream_ptr(x.device)),
+          "dav2_conv3x3_bf16")
+    return (out, out_relu) if want_relu else out
+
+
+def attention_bf16(qkv: torch.Tensor, B: int, N: int, D: int) -> torch.Tensor:
+    """qkv bf16 [B*N, 3D] (q pre-scaled) -> softmax(q k^T) v, bf16 [B*N, D]; heads of 64."""
+    require_cuda(qkv, "qkv")
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * N, 3 * D)
+    out = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.load().dav2_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, N, D, current_stream_ptr(qkv.device)),
+          "dav2_attention_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    require_cuda(x, "x")
+    assert x.dtype == torch.float32
+    rows, D = x.shape
+    out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().dav2_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, D, eps,
+                                     current_stream_ptr(x.device)), "dav2_layernorm")
+    return out
+
+
+def bilinear_nhwc_bf16(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    require_cuda(x, "x")
+    B, Hi, Wi, Cc = x.shape
+    out = torch.empty(B, Ho, Wo, Cc, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().dav2_bilinear_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, Cc,
+                                              current_stream_ptr(x.device)), "dav2_bilinear_nhwc_bf16")
+    return out
+
+
+def resize_depth(depth: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    """F.interpolate(depth[:,None], (Ho,Wo), mode='bilinear', align_corners=True)[:,0] for fp32 [B,H,W]."""
+    require_cuda(depth, "depth")
+    assert depth.dtype == torch.float32 and depth.dim() == 3
+    B, Hi, Wi = depth.shape
+    out = torch.empty(B, Ho, Wo, dtype=torch.float32, device=depth.device)
+    check(_lib.load().dav2_resize_depth(depth.data_ptr(), B, Hi, Wi, out.data_ptr(), Ho, Wo,
+                                        current_stream_ptr(depth.device)), "dav2_resize_depth")
+    return out
+
+
+def backproject(depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, depth_trunc: float = math.inf,
+                want_valid: bool = True, want_counts: bool = True, out_xyz: torch.Tensor | None = None):
+    """depth fp32 [B,H,W] -> (xyz fp32 [B,H*W,3], valid u8 [B,H*W] | None, counts i32 [B] | None).
+
+    K4: (fx,fy,cx,cy) tuple, or fp64 tensor [4] / [B,4]; T12: fp64 tensor [B,12] of row-major [R|t] or None."""
+    require_cuda(depth, "depth")
+    assert depth.dtype == torch.float32 and depth.dim() == 3
+    B, H, W = depth.shape
+    dev = depth.device
+    if not torch.is_tensor(K4):
+        K4 = torch.tensor([float(v) for v in K4], dtype=torch.float64)
+    K4 = K4.to(device=dev, dtype=torch.float64).contiguous()
+    k_per_frame = 1 if K4.dim() == 2 else 0
+    if k_per_frame:
+        assert K4.shape == (B, 4)
+    if T12 is not None:
+        T12 = T12.to(device=dev, dtype=torch.float64).contiguous()
+        assert T12.shape == (B, 12)
+    xyz = out_xyz if out_xyz is not None else torch.empty(B, H * W, 3, dtype=torch.float32, device=dev)
+    valid = torch.empty(B, H * W, dtype=torch.uint8, device=dev) if want_valid else None
+    counts = torch.empty(B, dtype=torch.int32, device=dev) if want_counts else None
+    check(_lib.load().dav2_backproject(depth.data_ptr(), B, H, W, K4.data_ptr(), k_per_frame, _ptr(T12),
+                                       float(depth_scale), float(depth_trunc), xyz.data_ptr(), _ptr(valid), _ptr(counts),
+                                       current_stream_ptr(dev)), "dav2_backproject")
+    return xyz, valid, counts
+
+
+def depth_metric_partials(pred: torch.Tensor, gt: torch.Tensor, lo: float, hi: float, variant: int,
+                          per_frame: bool) -> torch.Tensor:
+    """fp64 partial sums [B,8] or [8] (see include/dav2_b200.h) for pred/gt fp32 [B, ...]."""
+    require_cuda(pred, "pred"); require_cuda(gt, "gt")
+    assert pred.dtype == torch.float32 and gt.dtype == torch.float32 and pred.shape == gt.shape
+    B = pred.shape[0] if pred.dim() > 1 else 1
+    HW = pred.numel() // B
+    out = torch.empty((B, 8) if per_frame else (8,), dtype=torch.float64, device=pred.device)
+    check(_lib.load().dav2_depth_metrics(pred.data_ptr(), gt.data_ptr(), B, HW, float(lo), float(hi), int(variant),
+                                         1 if per_frame else 0, out.data_ptr(), current_stream_ptr(pred.device)),
+          "dav2_depth_metrics")
+    return out
+
+
+def compose_poses(rel: torch.Tensor, init7: torch.Tensor | None = None, want_T12: bool = False):
+    require_cuda(rel, "rel")
+    assert rel.dtype == torch.float32 and rel.dim() == 2 and rel.shape[1] == 7
+    N = rel.shape[0]
+    abs7 = torch.empty(N + 1, 7, dtype=torch.float32, device=rel.device)
+    T12 = torch.empty(N + 1, 12, dtype=torch.float64, device=rel.device) if want_T12 else None
+    if init7 is not None:
+        init7 = init7.to(device=rel.device, dtype=torch.float32).reshape(-1).contiguous()
+        assert init7.numel() == 7
+    check(_lib.load().dav2_compose_poses(rel.data_ptr(), _ptr(init7), N, abs7.data_ptr(), _ptr(T12),
+                                         current_stream_ptr(rel.device)), "dav2_compose_poses")
+    return (abs7, T12) if want_T12 else abs7

@@ -1,0 +1,133 @@
+/* dav2_b200 -- C ABI of the B200-native depth + point-cloud hot path.
+ *
+ * Drop-in boundary.  The reference (prototypeanugrah/Enhanced-3D-Reconstruction-in-Colonoscopy-...)
+ * is pure Python and has no FFI layer of its own; the hot path sits behind Python call signatures
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  The Python mirror of those interfaces lives in the
+ * package (dpt.py, depth_to_pointcloud.py, evaluation.py, calculate_metrics.py) and binds this
+ * library with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer documented as "device" is a CUDA device pointer owned by the
+ *     CALLER (e.g. a torch tensor's data_ptr()); the library never frees caller memory;
+ *   - the library owns its packed weights and workspace (allocated lazily, released by dav2_destroy);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *     no call synchronises except dav2_create / dav2_set_weight (host-side packing + H2D copy);
+ *   - return 0 on success, <0 on error; dav2_last_error() returns a thread-local message;
+ *   - one handle per (device, host thread); a handle is not thread-safe;
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef DAV2_B200_H
+#define DAV2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dav2_model dav2_model;
+
+/* DepthAnythingV2(encoder, features, out_channels, use_bn=False, use_clstoken=False, max_depth)
+ * -- external dpt.DepthAnythingV2.__init__, called at run.py:120-125, lightning_model.py:116-121,
+ *    depth_to_pointcloud_dav2.py:159-164. */
+typedef struct dav2_config {
+  int32_t embed_dim;      /* 384 / 768 / 1024 (vits / vitb / vitl)            */
+  int32_t depth;          /* 12 / 12 / 24 transformer blocks                   */
+  int32_t num_heads;      /* 6 / 12 / 16 (head dim is always 64)               */
+  int32_t features;       /* DPT width: 64 / 128 / 256                         */
+  int32_t out_channels[4];/* reassemble widths, run.py:97-118                  */
+  int32_t tap_layers[4];  /* 0-based block indices tapped for the DPT head     */
+  float max_depth;        /* sigmoid scale, run.py:76 / configs/model/large.yaml:3 */
+} dav2_config;
+
+int dav2_create(dav2_model** out, const dav2_config* cfg);
+void dav2_destroy(dav2_model* m);
+
+/* load_state_dict (run.py:128-147, lightning_model.py:130-140): one call per upstream state-dict
+ * key ("pretrained.blocks.3.attn.qkv.weight", ...).  `data` is HOST fp32, C-contiguous, `shape`
+ * its dims.  The library converts / re-lays-out into its kernel formats (bf16 K-major GEMM operands,
+ * tap-major 3x3 filters, pixel-shuffle-major transposed-conv filters, q pre-scaled by 1/8).
+ * Unknown keys return a negative code (the Python layer implements strict=False on top). */
+int dav2_set_weight(dav2_model* m, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+/* 1 once every tensor the forward pass needs has been supplied. */
+int dav2_weights_complete(const dav2_model* m);
+/* Position-embedding table for a ph x pw patch grid other than the checkpoint's 37x37: HOST fp32
+ * [1 + ph*pw, embed_dim] (bicubic interpolation of the checkpoint table is input independent, so the
+ * host layer computes it once per resolution exactly like upstream interpolate_pos_encoding). */
+int dav2_set_pos_embed(dav2_model* m, int32_t ph, int32_t pw, const float* table);
+
+/* DepthAnythingV2.forward(x[B,3,H,W]) -> depth[B,H,W]   (lightning_model.py:301, :358; external dpt.py)
+ * x: device fp32 NCHW, already ImageNet-normalised; H, W multiples of 14.  depth: device fp32. */
+int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W, float* depth, void* stream);
+
+/* Parity / debugging: look up an internal activation buffer of the LAST forward by name
+ * ("tap0".."tap3" bf16 [B*ph*pw, D]; "x" fp32 residual stream; "path1" ...).  Returns device ptr + bytes. */
+int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* bytes);
+
+/* infer_image's final F.interpolate(depth[:,None], (h,w), mode="bilinear", align_corners=True)
+ * (external dpt.py infer_image; used at run.py:234).  Device fp32 in/out. */
+int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float* out, int32_t Ho, int32_t Wo,
+                      void* stream);
+
+/* Fused back-projection + SE(3) world transform + validity mask.
+ * Replaces depth_to_pointcloud.py:218-239 (Open3D RGBD -> PointCloud.create_from_rgbd_image -> transform)
+ * and the explicit formula at depth_to_pointcloud_dav2.py:300-313.
+ *   depth  device fp32 [B,H,W]
+ *   K4     device fp64 [B,4] (k_per_frame=1) or [4] (k_per_frame=0): fx, fy, cx, cy
+ *   T12    device fp64 [B,12] row-major [R|t] (depth_to_pointcloud.py:170-173) or NULL (camera frame)
+ *   z = depth / depth_scale; pixel valid iff 0 < z < depth_trunc and finite (Open3D defaults 1000 / 3.0;
+ *   pass depth_scale=1, depth_trunc=INFINITY for metric depth straight from the network)
+ *   xyz    device fp32 [B,H*W,3] dense, row-major pixels (invalid -> 0,0,0)
+ *   valid  device u8   [B,H*W] or NULL;   counts device i32 [B] or NULL (# valid points per frame) */
+int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
+                     const double* T12, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
+                     int32_t* counts, void* stream);
+
+/* Depth-metric partial sums (finalise on the host AFTER any cross-GPU sum).
+ *   variant 0: evaluation.compute_errors on the batch-wide mask lo <= gt <= hi
+ *              (eval/evaluation.py:16-60, lightning_model.py:304-313)
+ *   variant 1: calculate_metrics.calculate_metrics mask gt>0 & pred>0 & finite (calculate_metrics.py:17-55)
+ *   variant 2: evaluation.compute_errors on inputs the caller already masked (every element counts)
+ *   partials   device fp64 [B,8] (per_frame=1) or [8]:
+ *              {n, sum|d|, sum|d|/(gt+1e-6), sum d^2, sum gt, #(t<a), #(t<b), #(t<c)}, t = max(gt/pred, pred/gt),
+ *              (a,b,c) = (1.25, 1.25^2, 1.25^3) for variant 1; for variants 0 and 2 slot 5 is #(t<1.1) and
+ *              slots 6, 7 count NaN / Inf predictions (the warnings of eval/evaluation.py:33-36). */
+int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float lo, float hi,
+                       int32_t variant, int32_t per_frame, double* partials, void* stream);
+
+/* evaluation.compose_poses (eval/evaluation.py:279-382): rel device fp32 [N,7] (t | q xyzw),
+ * init7 device fp32 [7] or NULL (identity) -> abs7 device fp32 [N+1,7]; optional T12 device fp64
+ * [N+1,12] = rows of [R|t] with R = Rotation.from_quat(q).as_matrix() (depth_to_pointcloud.py:168-173). */
+int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* abs7, double* T12, void* stream);
+
+/* Operator-level entry points (unit parity tests + reuse): bf16 device operands.
+ *   C[M,N] = act(A[M,K] * W[N,K]^T + bias)    A, W, C bf16 row-major; bias fp32 or NULL; act 0/1(GELU)/2(ReLU) */
+int dav2_linear_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                     int32_t act, void* stream);
+/*   x[M,N](fp32) += gamma[N] * (A[M,K] * W[N,K]^T + bias[N])   (LayerScale + residual epilogue) */
+int dav2_linear_resid(const void* A, const void* W, const float* bias, const float* gamma, float* x, int32_t M,
+                      int32_t N, int32_t K, void* stream);
+/*   3x3 / pad 1 / stride 1 conv, NHWC bf16: in [B,H,W,Cin], Wp [Cout, 9*Cpad] (tap-major, Cpad = ceil64(Cin)),
+ *   out [B,H,W,Cout] = act(conv + bias) + add1 + add2; out_relu (optional) = relu(out). */
+int dav2_conv3x3_bf16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
+                      void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                      int32_t act, void* stream);
+/*   softmax(q k^T) v per (image, head), d_head 64, q pre-scaled: qkv bf16 [B*N, 3*D] -> out bf16 [B*N, D] */
+int dav2_attention_bf16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, void* stream);
+/*   LayerNorm(eps) fp32 [rows, D] -> bf16 */
+int dav2_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t D, float eps,
+                   void* stream);
+/*   bilinear align_corners=True, NHWC bf16 */
+int dav2_bilinear_nhwc_bf16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                            int32_t C, void* stream);
+
+const char* dav2_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t dav2_launch_count(void);
+const char* dav2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAV2_B200_H */

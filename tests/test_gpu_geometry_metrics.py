@@ -1,0 +1,213 @@
+"""GPU parity (through the C ABI) for the HBM-bound kernels: back-projection + SE(3), metric
+reductions, pose chain -- against the oracle and the reference-generated golden fixtures."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_oracle as geo
+from oracle import metrics_oracle as met
+
+pytestmark = pytest.mark.gpu
+
+CM_KEYS = ("rmse", "mae", "abs_rel", "sq_rel", "delta1", "delta2", "delta3")
+CE_KEYS = ("d1", "abs_rel", "rmse", "l1")
+POINT_RTOL = 1e-5   # north_star: point coordinates within 1e-5 relative given identical depth
+METRIC_TOL = 1e-4   # north_star: metric values within 1e-4
+
+
+def _rel_err_points(a, b):
+    """relative error measured on the point norm, per point."""
+    na = np.linalg.norm(b, axis=-1)
+    return np.linalg.norm(a - b, axis=-1) / np.maximum(na, 1e-12)
+
+
+def test_backproject_golden_fixture(golden_dir):
+    from dav2_b200 import ops
+    g = np.load(os.path.join(golden_dir, "backproject_small.npz"))
+    d = torch.from_numpy(g["depth"])[None].cuda()
+    xyz, valid, counts = ops.backproject(d, tuple(g["k4"]))
+    v = valid[0].bool().cpu().numpy()
+    assert (v == (g["depth"].reshape(-1) > 0)).all() and int(counts[0]) == int(v.sum())
+    assert _rel_err_points(xyz[0].cpu().numpy()[v].astype(np.float64), g["points"][v]).max() < POINT_RTOL
+    T12 = torch.from_numpy(g["T"][:3, :4].reshape(1, 12))
+    w, _, _ = ops.backproject(d, tuple(g["k4"]), T12)
+    assert _rel_err_points(w[0].cpu().numpy()[v].astype(np.float64), g["world"][v]).max() < POINT_RTOL
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 1, 1), (2, 7, 5), (3, 37, 53), (2, 518, 518)])
+def test_backproject_vs_oracle(B, H, W):
+    from dav2_b200 import ops
+    rng = np.random.default_rng(B * 1000 + H)
+    depth = np.clip(rng.gamma(2.0, 0.03, size=(B, H, W)), 0, 0.2).astype(np.float32)
+    depth[rng.random((B, H, W)) < 0.05] = 0.0
+    if H * W > 4:
+        depth[0].reshape(-1)[1] = np.nan
+        depth[0].reshape(-1)[2] = np.inf
+        depth[0].reshape(-1)[3] = -1.0
+    k4 = geo.scale_intrinsics(geo.SIMCOL_K_475, 475, max(W, 2))
+    Ts = []
+    for b in range(B):
+        q = rng.normal(size=4)
+        Ts.append(geo.make_transform(rng.normal(size=3), q))
+    T12 = torch.from_numpy(np.stack([T[:3, :4].reshape(-1) for T in Ts]))
+    xyz, valid, counts = ops.backproject(torch.from_numpy(depth).cuda(), k4, T12)
+    for b in range(B):
+        ref, rv = geo.backproject(depth[b], k4, Ts[b])
+        got = xyz[b].cpu().numpy().astype(np.float64)
+        gv = valid[b].bool().cpu().numpy()
+        assert (gv == rv).all()
+        assert int(counts[b]) == int(rv.sum())
+        if rv.any():
+            assert _rel_err_points(got[rv], ref[rv]).max() < POINT_RTOL
+        assert (got[~rv] == 0).all()
+
+
+def test_backproject_open3d_scale_trunc():
+    from dav2_b200 import ops
+    d = torch.tensor([[[0.0, 500.0, 2999.0, 3000.0, 65535.0, 1.0, 2.0]]]).cuda()
+    xyz, valid, counts = ops.backproject(d, (100.0, 100.0, 2.0, 0.0), None, 1000.0, 3.0)
+    assert valid[0].tolist() == [0, 1, 1, 0, 0, 1, 1] and int(counts[0]) == 4
+    np.testing.assert_allclose(xyz[0, 1].cpu().numpy(), [(1 - 2) * 0.5 / 100, 0.0, 0.5], rtol=1e-6)
+
+
+def test_backproject_full_size_properties():
+    """BASELINE full size (64 x 518^2): size-independent properties instead of an oracle pass."""
+    from dav2_b200 import ops
+    B, H, W = 64, 518, 518
+    g = torch.Generator(device="cuda").manual_seed(5)
+    depth = torch.rand(B, H, W, generator=g, device="cuda") * 0.2
+    depth[:, ::7, ::5] = 0.0
+    k4 = geo.scale_intrinsics(geo.SIMCOL_K_475)
+    xyz, valid, counts = ops.backproject(depth, k4)
+    assert torch.equal(valid.view(B, H, W).bool(), depth > 0)
+    assert torch.equal(counts.long(), (depth > 0).view(B, -1).sum(1))
+    # z channel is the depth itself (identity pose); x/z is the pixel ray, independent of depth (linearity)
+    assert torch.equal(xyz[..., 2].view(B, H, W), depth)
+    xyz2, _, _ = ops.backproject(depth * 2, k4)
+    m = valid.bool()
+    assert torch.allclose(xyz2[m], 2 * xyz[m], rtol=1e-6, atol=0)
+    # rigid transform preserves pairwise distances: rotate by a pose and compare norms about the centroid
+    T = geo.make_transform([0.3, -0.2, 0.1], [0.1, 0.2, 0.3, 0.9])
+    T12 = torch.from_numpy(np.tile(T[:3, :4].reshape(1, 12), (B, 1)))
+    w, _, _ = ops.backproject(depth, k4, T12)
+    a = (xyz[0][m[0]].double() - torch.tensor(0.0)).norm(dim=1)
+    b = (w[0][m[0]].double() - torch.tensor(T[:3, 3]).cuda()).norm(dim=1)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_metrics_golden_fixture(golden_dir):
+    from dav2_b200 import calculate_metrics as cm
+    from dav2_b200 import evaluation as ev
+    g = np.load(os.path.join(golden_dir, "metrics_small.npz"))
+    rows = cm.calculate_metrics_batch(g["gt"], g["pred"])
+    for b, m in enumerate(rows):
+        np.testing.assert_allclose([m[k] for k in CM_KEYS], g["calculate_metrics"][b], rtol=METRIC_TOL, atol=1e-7)
+    one = cm.calculate_metrics(g["gt"][1], g["pred"][1])
+    np.testing.assert_allclose([one[k] for k in CM_KEYS], g["calculate_metrics"][1], rtol=METRIC_TOL, atol=1e-7)
+    gt, pred = torch.from_numpy(g["gt"]).cuda()[:, None], torch.from_numpy(g["pred"]).cuda()[:, None]
+    fused = ev.test_step_metrics(pred, gt, 1e-6, 20.0)
+    np.testing.assert_allclose([float(fused[k]) for k in CE_KEYS], g["compute_errors"], rtol=METRIC_TOL, atol=1e-7)
+    mask = (gt >= 1e-6) & (gt <= 20.0)
+    plain = ev.compute_errors(pred[mask].flatten(), gt[mask].flatten())
+    np.testing.assert_allclose([float(plain[k]) for k in CE_KEYS], g["compute_errors"], rtol=METRIC_TOL, atol=1e-7)
+    assert plain["d1"].dim() == 0 and plain["d1"].is_cuda and plain["d1"].dtype == torch.float32
+
+
+def test_metrics_empty_and_nonfinite():
+    from dav2_b200 import calculate_metrics as cm
+    from dav2_b200 import evaluation as ev
+    m = cm.calculate_metrics(np.zeros((4, 4), np.float32), np.ones((4, 4), np.float32))
+    assert all(math.isnan(v) for v in m.values())
+    pred = torch.tensor([1.0, float("nan"), 2.0, float("inf")]).cuda()
+    gt = torch.tensor([1.0, 1.0, 2.0, 1.0]).cuda()
+    out = ev.compute_errors(pred, gt)
+    ref = met.compute_errors(pred.cpu().numpy(), gt.cpu().numpy())
+    assert math.isnan(float(out["l1"])) == math.isnan(ref["l1"])
+    np.testing.assert_allclose(float(out["d1"]), ref["d1"], rtol=1e-6)
+    e = ev.compute_errors(torch.zeros(0).cuda(), torch.zeros(0).cuda())
+    assert math.isnan(float(e["rmse"]))
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 3, 5), (4, 70, 98), (32, 518, 518)])
+def test_metrics_vs_oracle(B, H, W):
+    from dav2_b200 import calculate_metrics as cm
+    from dav2_b200 import evaluation as ev
+    rng = np.random.default_rng(B + H)
+    gt = np.clip(rng.gamma(2.0, 0.15, size=(B, 1, H, W)), 0, 1).astype(np.float32)
+    gt[rng.random(gt.shape) < 0.02] = 0.0
+    pred = (np.where(gt > 0, gt, 0.3) * rng.normal(1.0, 0.07, size=gt.shape)).astype(np.float32)
+    ref = met.test_step_metrics(pred, gt, 1e-6, 20.0)
+    got = ev.test_step_metrics(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), 1e-6, 20.0)
+    for k in CE_KEYS:
+        assert abs(float(got[k]) - ref[k]) <= METRIC_TOL * max(1.0, abs(ref[k])), k
+    nb = min(B, 3)
+    rows = cm.calculate_metrics_batch(gt[:nb, 0], pred[:nb, 0])
+    for b in range(nb):
+        r = met.calculate_metrics(gt[b, 0], pred[b, 0])
+        for k in CM_KEYS:
+            assert abs(rows[b][k] - r[k]) <= METRIC_TOL * max(1.0, abs(r[k])), k
+    # sharding property (multi-GPU contract): partial sums over frame slices add up to the whole batch
+    if B >= 2:
+        p, g = torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda()
+        whole = ev.metric_partials(p, g)
+        parts = ev.metric_partials(p[: B // 2].contiguous(), g[: B // 2].contiguous()) + \
+            ev.metric_partials(p[B // 2:].contiguous(), g[B // 2:].contiguous())
+        assert torch.allclose(whole, parts, rtol=1e-12)
+
+
+def test_compose_poses_golden(golden_dir):
+    from dav2_b200 import evaluation as ev
+    from dav2_b200 import ops
+    g = np.load(os.path.join(golden_dir, "poses_small.npz"))
+    rel = torch.from_numpy(g["rel"]).cuda()
+    np.testing.assert_allclose(ev.compose_poses(rel).cpu().numpy(), g["abs"], rtol=1e-5, atol=1e-6)
+    a, T12 = ops.compose_poses(rel, torch.from_numpy(g["init"]).cuda(), want_T12=True)
+    np.testing.assert_allclose(a.cpu().numpy(), g["abs_init"], rtol=1e-5, atol=1e-6)
+    # 3-D input uses batch 0 only; 1-D input is a single step
+    np.testing.assert_allclose(ev.compose_poses(torch.stack([rel, rel * 0])).cpu().numpy(), g["abs"], rtol=1e-5, atol=1e-6)
+    assert ev.compose_poses(rel[0]).shape == (2, 7)
+    T = T12.cpu().numpy()
+    np.testing.assert_allclose(T[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3, 3), g["rot"], atol=1e-6)
+    np.testing.assert_allclose(T[:, [3, 7, 11]], g["abs_init"][:, :3], atol=1e-7)
+    # long chain (config 4: ~1000 frames) against the oracle
+    rng = np.random.default_rng(1)
+    N = 1000
+    q = rng.normal(size=(N, 4)); q[:, 3] += 8; q /= np.linalg.norm(q, axis=1, keepdims=True)
+    relN = np.concatenate([rng.normal(0, 0.01, size=(N, 3)), q], axis=1).astype(np.float32)
+    got = ev.compose_poses(torch.from_numpy(relN).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, geo.compose_poses(relN), rtol=1e-4, atol=1e-5)
+
+
+def test_point_cloud_api(tmp_path, golden_dir):
+    """generate_point_cloud / load_* signatures on files (Open3D semantics: z=d/1000, z>=3 dropped, BGR colours)."""
+    import cv2
+    from dav2_b200 import depth_to_pointcloud as d2p
+    rng = np.random.default_rng(3)
+    root = tmp_path / "SyntheticColon_I"
+    (root / "Frames_S1").mkdir(parents=True)
+    H = W = 32
+    depth = rng.integers(0, 4000, size=(H, W)).astype(np.uint16)
+    color = rng.integers(0, 255, size=(H, W, 3)).astype(np.uint8)
+    cv2.imwrite(str(root / "Frames_S1" / "Depth_0000.png"), depth)
+    cv2.imwrite(str(root / "Frames_S1" / "FrameBuffer_0000.png"), color)
+    (root / "cam.txt").write_text("20.0,0,15.5,0,21.0,16.5,0,0,1")
+    (root / "SavedPosition_S1.txt").write_text("0.1 0.2 0.3\n1 2 3\n")
+    (root / "SavedRotationQuaternion_S1.txt").write_text("0.1 0.2 0.3 0.9\n0 0 0 1\n")
+    rgb = str(root / "Frames_S1" / "FrameBuffer_0000.png")
+    cam, pos, rot = d2p.get_procedure_files(rgb)
+    pc = d2p.generate_point_cloud(str(root / "Frames_S1" / "Depth_0000.png"), rgb, cam, pos, rot, 0)
+    T = geo.make_transform([0.1, 0.2, 0.3], [0.1, 0.2, 0.3, 0.9])
+    np.testing.assert_allclose(d2p.load_transformation(pos, rot, 0), T, atol=1e-12)
+    ref, rv = geo.backproject(depth, (20.0, 21.0, 15.5, 16.5), T, depth_scale=1000.0, depth_trunc=3.0)
+    assert len(pc) == int(rv.sum())
+    assert _rel_err_points(pc.points, ref[rv]).max() < POINT_RTOL
+    np.testing.assert_allclose(pc.colors, color.reshape(-1, 3)[rv] / 255.0, atol=1e-6)
+    both = d2p.PointCloud()
+    both += pc
+    both += pc
+    assert len(both) == 2 * len(pc) and both.points.shape == (2 * len(pc), 3)
+    d2p.write_ply(str(tmp_path / "c.ply"), both)
+    assert os.path.getsize(tmp_path / "c.ply") > 27 * len(both)
