@@ -31,6 +31,7 @@ SIGNATURES = {
     "dav2_set_pos_embed": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dav2_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dav2_debug_buffer": (c_int, [c_void_p, C.c_char_p, C.POINTER(c_void_p), C.POINTER(c_i64)]),
+    "dav2_debug_read": (c_int, [c_void_p, C.c_char_p, c_void_p, c_i64, c_void_p]),
     "dav2_resize_depth": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dav2_backproject": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -43,6 +44,8 @@ SIGNATURES = {
     "dav2_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dav2_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
     "dav2_bilinear_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_profile_enable": (None, [c_int]),
+    "dav2_profile_report": (c_int, [C.c_char_p, c_int]),
     "dav2_last_error": (C.c_char_p, []),
     "dav2_launch_count": (c_i64, []),
     "dav2_version": (C.c_char_p, []),
@@ -72,6 +75,18 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().dav2_last_error().decode(errors="replace")
         raise Dav2Error(f"{what or 'dav2 call'} failed (rc={rc}): {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    load().dav2_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    import json
+
+    buf = C.create_string_buffer(8192)
+    check(load().dav2_profile_report(buf, len(buf)), "dav2_profile_report")
+    return json.loads(buf.value.decode())
 
 
 def launch_count() -> int:

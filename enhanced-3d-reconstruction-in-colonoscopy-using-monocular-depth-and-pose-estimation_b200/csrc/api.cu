@@ -69,6 +69,11 @@ int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* byte
   return m->impl.debug_buffer(name, ptr, bytes);
 }
 
+int dav2_debug_read(dav2_model* m, const char* name, void* dst, int64_t bytes, void* stream) {
+  DAV2_CHECK(m && name && dst, "dav2_debug_read: null argument");
+  return m->impl.debug_read(name, dst, bytes, S(stream));
+}
+
 int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float* out, int32_t Ho, int32_t Wo,
                       void* stream) {
   DAV2_CHECK(in && out, "dav2_resize_depth: null pointer");
@@ -154,3 +159,8 @@ int64_t dav2_launch_count(void) { return launch_count(); }
 const char* dav2_version(void) { return "dav2_b200 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
 
 }  // extern "C"
+
+extern "C" {
+void dav2_profile_enable(int32_t on) { prof_enable(on); }
+int dav2_profile_report(char* buf, int32_t cap) { return prof_report(buf, cap); }
+}

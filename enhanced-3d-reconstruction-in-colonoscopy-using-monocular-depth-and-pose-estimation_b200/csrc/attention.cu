@@ -251,6 +251,7 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int N, int D, cudaStream
   p.v_lbo = v_lbo;
   p.v_sbo = v_sbo;
   dim3 grid((N + 127) / 128, D / 64, B);
+  ProfScope ps(PC_ATTN, 4.0 * B * (D / 64) * (double)N * N * 64.0, 2.0 * 4.0 * B * (double)N * D, stream);
   attention_kernel<<<grid, 192, ATT_SMEM, stream>>>(tm, p);
   DAV2_LAUNCH_OK();
   return 0;

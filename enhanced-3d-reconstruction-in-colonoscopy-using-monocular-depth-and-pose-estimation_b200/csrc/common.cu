@@ -89,3 +89,48 @@ int sm_count() {
 }
 
 }  // namespace dav2
+
+// ----------------------------------------------------------------------------------------------
+// per-kernel-class event timing
+// ----------------------------------------------------------------------------------------------
+#include <vector>
+namespace dav2 {
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+static const char* kClassNames[PC_COUNT] = {"gemm_tcgen05", "conv_tcgen05", "attention_tcgen05", "layernorm", "resample",
+                                            "im2col", "backproject", "depth_metrics", "other"};
+void prof_enable(int on) { g_prof = on != 0; }
+bool prof_enabled() { return g_prof; }
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int cls, double flops, double bytes, cudaStream_t stream) {
+  ProfRec r; r.cls = cls; r.flops = flops; r.bytes = bytes; r.a = get_event(); r.b = get_event();
+  cudaEventRecord(r.a, stream);
+  g_recs.push_back(r);
+}
+void prof_end(cudaStream_t stream) { if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, stream); }
+int prof_report(char* buf, int cap) {
+  double ms[PC_COUNT] = {0}, fl[PC_COUNT] = {0}, by[PC_COUNT] = {0}; long long n[PC_COUNT] = {0};
+  for (auto& r : g_recs) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f; cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t; fl[r.cls] += r.flops; by[r.cls] += r.bytes; n[r.cls] += 1;
+    g_pool.push_back(r.a); g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  int off = snprintf(buf, cap, "{");
+  bool first = true;
+  for (int c = 0; c < PC_COUNT && off < cap; ++c) {
+    if (!n[c]) continue;
+    off += snprintf(buf + off, cap - off, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                    first ? "" : ", ", kClassNames[c], n[c], ms[c], fl[c], by[c]);
+    first = false;
+  }
+  if (off < cap) off += snprintf(buf + off, cap - off, "}");
+  return off < cap ? 0 : -1;
+}
+}  // namespace dav2

@@ -206,3 +206,26 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
 int sm_count();
 
 }  // namespace dav2
+
+// ----------------------------------------------------------------------------------------------
+// optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+// ----------------------------------------------------------------------------------------------
+namespace dav2 {
+enum ProfClass { PC_GEMM = 0, PC_CONV, PC_ATTN, PC_LAYERNORM, PC_RESAMPLE, PC_IM2COL, PC_BACKPROJECT, PC_METRICS, PC_OTHER, PC_COUNT };
+void prof_enable(int on);
+bool prof_enabled();
+void prof_begin(int cls, double flops, double bytes, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+// synchronises, accumulates and clears the pending events; writes one JSON object into buf
+int prof_report(char* buf, int cap);
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream) : s(stream), on(prof_enabled()) {
+    if (on) prof_begin(cls, flops, bytes, s);
+  }
+  ~ProfScope() {
+    if (on) prof_end(s);
+  }
+};
+}  // namespace dav2

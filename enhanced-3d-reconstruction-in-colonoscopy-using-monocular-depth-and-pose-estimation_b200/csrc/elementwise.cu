@@ -67,6 +67,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, bf16* out, 
   long long blocks = (rows + wpb - 1) / wpb;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_LAYERNORM, 0.0, (double)rows * D * 6.0, stream);
 #define LN_CASE(V)                                                                                             \
   case V:                                                                                                      \
     layernorm_kernel<V><<<(int)blocks, wpb * 32, 0, stream>>>(x, w, b, out, rows, rows_per_img, skip_cls, eps); \
@@ -113,6 +114,7 @@ int launch_patch_im2col(const float* x, bf16* A, int B, int H, int W, int KP, cu
   long long blocks = (nseg + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_IM2COL, 0.0, (double)B * 3 * H * W * 4.0 + (double)B * ph * pw * KP * 2.0, stream);
   patch_im2col_kernel<<<(int)blocks, 256, 0, stream>>>(x, A, B, H, W, ph, pw, KP);
   DAV2_LAUNCH_OK();
   return 0;
@@ -128,6 +130,7 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 }
 
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int ntok, int D, cudaStream_t stream) {
+  ProfScope ps(PC_OTHER, 0.0, (double)B * D * 12.0, stream);
   cls_row_kernel<<<(B * D + 255) / 256, 256, 0, stream>>>(x, cls, pos, B, ntok, D);
   DAV2_LAUNCH_OK();
   return 0;
@@ -165,6 +168,7 @@ int launch_im2col_s2(const bf16* in, bf16* A, int B, int H, int W, int C, cudaSt
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_IM2COL, 0.0, (double)total * 32.0, stream);
   im2col_s2_kernel<<<(int)blocks, 256, 0, stream>>>(in, A, B, H, W, C, Ho, Wo);
   DAV2_LAUNCH_OK();
   return 0;
@@ -221,6 +225,7 @@ int launch_bilinear_nhwc(const bf16* in, bf16* out, int B, int Hi, int Wi, int H
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_RESAMPLE, 0.0, 2.0 * C * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
   bilinear_nhwc_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, C, sy, sx);
   DAV2_LAUNCH_OK();
   return 0;
@@ -254,6 +259,7 @@ int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int 
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) return 0;
+  ProfScope ps(PC_RESAMPLE, 0.0, 4.0 * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
   bilinear_f32_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, sy, sx);
   DAV2_LAUNCH_OK();
   return 0;

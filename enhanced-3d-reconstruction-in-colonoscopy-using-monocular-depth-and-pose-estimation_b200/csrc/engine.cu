@@ -316,6 +316,7 @@ int gemm_linear(int mode, const bf16* A, int M, int K, long long lda, const bf16
   p.num_kb = (K + 63) / 64;
   p.tiles_m = (M + 127) / 128;
   p.tiles_n = (N + bn - 1) / bn;
+  ProfScope ps(PC_GEMM, 2.0 * M * (double)N * K, 2.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }
 
@@ -353,6 +354,7 @@ int conv3x3(int mode, const bf16* in, int B, int H, int W, int Cin, const bf16* 
   p.tiles_m = B * p.tiles_x * p.tiles_y;
   p.tiles_n = (Cout + bn - 1) / bn;
   if (p.ldo == 0) p.ldo = Cout;
+  ProfScope ps(PC_CONV, 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 2.0 * ((double)B * H * W * (Cin + Cout) + 9.0 * Cin * Cout), stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }
 
@@ -546,6 +548,14 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
     p.out = depth; p.bias = oc2_b; p.head_w = oc3_w; p.head_b = oc3_b; p.max_depth = cfg.max_depth;
     RC(conv3x3(GM_CONV_HEAD, O1U, B, H, W, F / 2, oc2_w, 32, p, stream));
   }
+  return 0;
+}
+
+int Model::debug_read(const char* name, void* dst, int64_t bytes, cudaStream_t stream) {
+  auto it = ws.find(name);
+  DAV2_CHECK(it != ws.end(), "debug_read: no buffer named '%s'", name);
+  DAV2_CHECK(bytes >= 0 && (size_t)bytes <= it->second.bytes, "debug_read: %lld bytes requested, buffer '%s' holds %zu", (long long)bytes, name, it->second.bytes);
+  DAV2_CUDA_OK(cudaMemcpyAsync(dst, it->second.p, (size_t)bytes, cudaMemcpyDeviceToDevice, stream));
   return 0;
 }
 

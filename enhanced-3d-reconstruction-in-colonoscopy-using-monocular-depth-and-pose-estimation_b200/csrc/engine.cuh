@@ -59,6 +59,7 @@ struct Model {
   int buf(const char* name, size_t bytes, void** out);
   int forward(const float* x, int B, int H, int W, float* depth, cudaStream_t stream);
   int debug_buffer(const char* name, void** ptr, int64_t* bytes);
+  int debug_read(const char* name, void* dst, int64_t bytes, cudaStream_t stream);
 };
 
 int gemm_linear(int mode, const bf16* A, int M, int K, long long lda, const bf16* Wt, int N, GemmParams p,

@@ -120,6 +120,7 @@ int launch_backproject(const float* depth, int B, int H, int W, const double* K4
   const long long cap = ((long long)sm_count() * 8 * 4 + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
+  ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (valid ? 17.0 : 16.0), stream);
   dim3 grid((unsigned)bx, (unsigned)B);
   if (vec)
     backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
@@ -210,13 +211,19 @@ __global__ void __launch_bounds__(256) depth_metrics_kernel(const float* __restr
 
 int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW, float lo, float hi, int variant,
                          int per_frame, double* partials, cudaStream_t stream) {
-  DAV2_CHECK(pred && gt && partials && B > 0 && HW > 0, "depth_metrics: null pointer or empty shape");
+  DAV2_CHECK(partials && B > 0 && HW >= 0, "depth_metrics: null pointer or bad shape");
+  if (HW == 0) {  // empty selection: all-zero partials (mean of nothing -> NaN after finalisation)
+    DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
+    return 0;
+  }
+  DAV2_CHECK(pred && gt, "depth_metrics: null pointer");
   DAV2_CHECK(variant >= 0 && variant <= 2, "depth_metrics: variant must be 0 (test_step mask), 1 (calculate_metrics) or 2 (no mask)");
   DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
   long long bx = (HW / 4 + 255) / 256;
   const long long cap = ((long long)sm_count() * 8 * 2 + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
+  ProfScope ps(PC_METRICS, 0.0, (double)B * HW * 8.0, stream);
   dim3 grid((unsigned)bx, (unsigned)B);
   if (variant == 0)
     depth_metrics_kernel<0><<<grid, 256, 0, stream>>>(pred, gt, HW, lo, hi, per_frame, partials);

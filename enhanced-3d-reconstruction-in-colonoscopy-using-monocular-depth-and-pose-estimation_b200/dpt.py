@@ -195,17 +195,11 @@ class DepthAnythingV2(nn.Module):
 
     def debug_buffer(self, name: str, dtype, shape) -> torch.Tensor:
         """Copy of an internal activation of the last forward (parity tests)."""
-        ptr, nbytes = C.c_void_p(), C.c_int64()
-        check(_lib.load().dav2_debug_buffer(self._handle, name.encode(), C.byref(ptr), C.byref(nbytes)), "dav2_debug_buffer")
-        n = int(np.prod(shape))
-        esize = torch.empty((), dtype=dtype).element_size()
-        assert n * esize <= nbytes.value, (name, n * esize, nbytes.value)
         dev = next(self.parameters()).device
         out = torch.empty(shape, dtype=dtype, device=dev)
-        torch.cuda.current_stream(dev).synchronize()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, n * esize, 3)  # cudaMemcpyDeviceToDevice
-        if int(rc) != 0:
-            raise Dav2Error(f"cudaMemcpy failed: {rc}")
+        with torch.cuda.device(dev):
+            check(_lib.load().dav2_debug_read(self._handle, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
+                                              _lib.current_stream_ptr(dev)), "dav2_debug_read")
         return out
 
     @torch.no_grad()

@@ -64,6 +64,8 @@ int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W,
 /* Parity / debugging: look up an internal activation buffer of the LAST forward by name
  * ("tap0".."tap3" bf16 [B*ph*pw, D]; "x" fp32 residual stream; "path1" ...).  Returns device ptr + bytes. */
 int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* bytes);
+/* Copy the first `bytes` of that buffer into caller-owned device memory `dst` (async on `stream`). */
+int dav2_debug_read(dav2_model* m, const char* name, void* dst, int64_t bytes, void* stream);
 
 /* infer_image's final F.interpolate(depth[:,None], (h,w), mode="bilinear", align_corners=True)
  * (external dpt.py infer_image; used at run.py:234).  Device fp32 in/out. */
@@ -121,6 +123,12 @@ int dav2_layernorm(const float* x, const float* w, const float* b, void* out, in
 /*   bilinear align_corners=True, NHWC bf16 */
 int dav2_bilinear_nhwc_bf16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
                             int32_t C, void* stream);
+
+/* Per-kernel-class timing with CUDA events recorded on the launching stream (bench.py's live roofline
+ * measurement).  dav2_profile_report synchronises on the pending events, then writes a JSON object
+ * {"gemm_tcgen05": {"launches":..,"ms":..,"flops":..,"bytes":..}, ...} (algorithmic flops / bytes). */
+void dav2_profile_enable(int32_t on);
+int dav2_profile_report(char* buf, int32_t cap);
 
 const char* dav2_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
