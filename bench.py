@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--encoder", default="vitl")
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--size", type=int, default=518)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="tensor-core operand format (fp16 = the reference's AMP 16-mixed; fp32 accumulate either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL cloud gather (N>1)")
     args = ap.parse_args()
@@ -194,7 +196,7 @@ def main():
     B, S = args.batch, args.size
     HW = S * S
 
-    model = DepthAnythingV2(**MODEL_CONFIGS[args.encoder], max_depth=20.0)
+    model = DepthAnythingV2(**MODEL_CONFIGS[args.encoder], max_depth=20.0, precision=args.precision)
     weights.randomize_(model, seed=0)
     cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     model = model.to(dev).eval()
@@ -329,7 +331,8 @@ def main():
                  for k, v in prof.items()}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16" if args.precision == "fp16" else "bf16",
         "data": "synthetic",
         "config": {"workload": f"BASELINE configs[2]: DepthAnythingV2 {args.encoder} batch {B}/GPU, {S}x{S} synthetic SimCol-shaped "
                                "frames, random-init weights; depth + pose chain + fused back-projection/SE(3)/validity + metric "

@@ -14,8 +14,11 @@ c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 class Dav2Config(C.Structure):
     _fields_ = [
         ("embed_dim", c_int), ("depth", c_int), ("num_heads", c_int), ("features", c_int),
-        ("out_channels", c_int * 4), ("tap_layers", c_int * 4), ("max_depth", c_float),
+        ("out_channels", c_int * 4), ("tap_layers", c_int * 4), ("max_depth", c_float), ("precision", c_int),
     ]
+
+
+FMT_F16, FMT_BF16 = 0, 1  # tensor-core operand formats (== include/dav2_b200.h `precision` / `fmt`)
 
 
 class Dav2Error(RuntimeError):
@@ -37,13 +40,13 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_depth_metrics": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
     "dav2_compose_poses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-    "dav2_linear_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dav2_linear_resid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "dav2_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "dav2_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "dav2_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
-    "dav2_bilinear_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_linear_h16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_linear_resid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_conv3x3_h16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_attention_h16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dav2_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_int, c_void_p]),
+    "dav2_bilinear_nhwc_h16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dav2_profile_enable": (None, [c_int]),
     "dav2_profile_report": (c_int, [C.c_char_p, c_int]),
     "dav2_last_error": (C.c_char_p, []),

@@ -29,6 +29,7 @@ int dav2_create(dav2_model** out, const dav2_config* cfg) {
   DAV2_CHECK(cfg->embed_dim % 128 == 0 && cfg->embed_dim <= 1024 && cfg->embed_dim == cfg->num_heads * 64,
              "dav2_create: embed_dim=%d heads=%d unsupported (need D = 64*heads, multiple of 128, <= 1024)",
              cfg->embed_dim, cfg->num_heads);
+  DAV2_CHECK(cfg->precision == 0 || cfg->precision == 1, "dav2_create: precision must be 0 (fp16) or 1 (bf16)");
   DAV2_CHECK(cfg->features % 16 == 0 && cfg->depth > 0, "dav2_create: features=%d depth=%d unsupported", cfg->features, cfg->depth);
   for (int i = 0; i < 4; ++i)
     DAV2_CHECK(cfg->out_channels[i] % 8 == 0 && cfg->tap_layers[i] >= 0 && cfg->tap_layers[i] < cfg->depth,
@@ -99,59 +100,70 @@ int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* a
   return launch_compose_poses(rel, init7, N, abs7, T12, S(stream));
 }
 
-int dav2_linear_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
-                     int32_t act, void* stream) {
+static int check_fmt(int32_t fmt) {
+  DAV2_CHECK(fmt == FMT_F16 || fmt == FMT_BF16, "fmt must be 0 (fp16) or 1 (bf16), got %d", fmt);
+  return 0;
+}
+
+int dav2_linear_h16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                    int32_t act, int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
-  DAV2_CHECK(A && W && C && K % 8 == 0, "dav2_linear_bf16: null pointer or K %% 8 != 0");
+  DAV2_CHECK(A && W && C && K % 8 == 0, "dav2_linear_h16: null pointer or K %% 8 != 0");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.out = C; p.ldo = N; p.bias = bias; p.act = act;
-  return gemm_linear(GM_LINEAR_BF16, (const bf16*)A, M, K, K, (const bf16*)W, N, p, S(stream));
+  p.out = C; p.ldo = N; p.bias = bias; p.act = act; p.fmt = fmt;
+  return gemm_linear(GM_LINEAR_BF16, (const h16*)A, M, K, K, (const h16*)W, N, p, S(stream));
 }
 
 int dav2_linear_resid(const void* A, const void* W, const float* bias, const float* gamma, float* x, int32_t M,
-                      int32_t N, int32_t K, void* stream) {
+                      int32_t N, int32_t K, int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
   DAV2_CHECK(A && W && x && gamma && K % 8 == 0, "dav2_linear_resid: null pointer or K %% 8 != 0");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.out = x; p.ldo = N; p.bias = bias; p.gamma = gamma;
-  return gemm_linear(GM_LINEAR_RESID, (const bf16*)A, M, K, K, (const bf16*)W, N, p, S(stream));
+  p.out = x; p.ldo = N; p.bias = bias; p.gamma = gamma; p.fmt = fmt;
+  return gemm_linear(GM_LINEAR_RESID, (const h16*)A, M, K, K, (const h16*)W, N, p, S(stream));
 }
 
-int dav2_conv3x3_bf16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
-                      void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                      int32_t act, void* stream) {
+int dav2_conv3x3_h16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
+                     void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                     int32_t act, int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
-  DAV2_CHECK(in && Wp && out, "dav2_conv3x3_bf16: null pointer");
+  DAV2_CHECK(in && Wp && out, "dav2_conv3x3_h16: null pointer");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.out = out; p.out_relu = (bf16*)out_relu; p.bias = bias; p.add1 = (const bf16*)add1; p.add2 = (const bf16*)add2;
-  p.act = act;
-  return conv3x3(GM_CONV_BF16, (const bf16*)in, B, H, W, Cin, (const bf16*)Wp, Cout, p, S(stream));
+  p.out = out; p.out_relu = (h16*)out_relu; p.bias = bias; p.add1 = (const h16*)add1; p.add2 = (const h16*)add2;
+  p.act = act; p.fmt = fmt;
+  return conv3x3(GM_CONV_BF16, (const h16*)in, B, H, W, Cin, (const h16*)Wp, Cout, p, S(stream));
 }
 
-int dav2_attention_bf16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, void* stream) {
+int dav2_attention_h16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
-  DAV2_CHECK(qkv && out, "dav2_attention_bf16: null pointer");
+  DAV2_CHECK(qkv && out, "dav2_attention_h16: null pointer");
   uint32_t lbo = 1024, sbo = 1024;
   if (const char* e = getenv("DAV2_ATT_VLBO")) lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("DAV2_ATT_VSBO")) sbo = (uint32_t)atoi(e);
-  return launch_attention((const bf16*)qkv, (bf16*)out, B, N, D, S(stream), lbo, sbo);
+  return launch_attention((const h16*)qkv, (h16*)out, B, N, D, fmt, S(stream), lbo, sbo);
 }
 
 int dav2_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t D, float eps,
-                   void* stream) {
+                   int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
   DAV2_CHECK(x && w && b && out, "dav2_layernorm: null pointer");
-  return launch_layernorm(x, w, b, (bf16*)out, rows, D, 1, 0, eps, S(stream));
+  return launch_layernorm(x, w, b, (h16*)out, rows, D, 1, 0, eps, fmt, S(stream));
 }
 
-int dav2_bilinear_nhwc_bf16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
-                            int32_t C, void* stream) {
+int dav2_bilinear_nhwc_h16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                           int32_t C, int32_t fmt, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
   if (int rc = require_sm100()) return rc;
-  DAV2_CHECK(in && out, "dav2_bilinear_nhwc_bf16: null pointer");
-  return launch_bilinear_nhwc((const bf16*)in, (bf16*)out, B, Hi, Wi, Ho, Wo, C, S(stream));
+  DAV2_CHECK(in && out, "dav2_bilinear_nhwc_h16: null pointer");
+  return launch_bilinear_nhwc((const h16*)in, (h16*)out, B, Hi, Wi, Ho, Wo, C, fmt, S(stream));
 }
 
 const char* dav2_last_error(void) { return get_last_error(); }

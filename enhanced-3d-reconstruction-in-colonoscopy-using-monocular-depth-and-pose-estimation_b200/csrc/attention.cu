@@ -7,23 +7,24 @@
 //                                     O_part = P V (128x64x128 -> TMEM cols [128,192)), V is the
 //                                     MN-major B operand straight from the [token, 3D] qkv buffer
 //   warps 2..5      : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
-//                                     fp32, P -> bf16 into 128B-swizzled smem (A operand of the PV MMA),
+//                                     fp32, P -> h16 into 128B-swizzled smem (A operand of the PV MMA),
 //                                     running O kept in registers (o = o*alpha + O_part)
 // Q was pre-scaled by d^-1/2 = 0.125 (folded exactly into the qkv weights), so S needs no scale.
-// Reads qkv bf16 [B*N, 3*D] (q | k | v, head h at columns h*64), writes out bf16 [B*N, D].
+// Reads qkv h16 [B*N, 3*D] (q | k | v, head h at columns h*64), writes out h16 [B*N, D].
 #include "common.cuh"
 
 namespace dav2 {
 
 struct AttnParams {
-  bf16* out;
+  h16* out;
   int N;      // tokens per image
   int D;      // model width (= heads * 64)
   int nkv;    // ceil(N / 128)
   uint32_t v_lbo, v_sbo;  // MN-major descriptor strides for V (bytes)
+  int fmt;                // FMT_F16 / FMT_BF16
 };
 
-static constexpr int ATT_TILE = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
+static constexpr int ATT_TILE = 128 * 64 * 2;  // 16 KB: one [128 x 64] h16 tile
 static constexpr int ATT_SMEM = 7 * ATT_TILE + 128;  // Q, K0, K1, V0, V1, P(2 tiles), barriers
 static constexpr float LOG2E = 1.4426950408889634f;
 
@@ -86,8 +87,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     }
   } else if (threadIdx.x == 32) {
     // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V   : V is MN-major
+    const uint32_t idesc_s = make_idesc_h(128, 128, 0, 0, p.fmt);  // S = Q K^T : both K-major
+    const uint32_t idesc_o = make_idesc_h(128, 64, 0, 1, p.fmt);   // O = P V   : V is MN-major
     const uint64_t qdesc = make_sw128_desc(sQ, 16, 1024);
     mbar_wait(BAR_Q, 0);
     mbar_wait(BAR_KV_FULL, 0);
@@ -95,7 +96,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     {
       const uint64_t kdesc = make_sw128_desc(sK, 16, 1024);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
+      for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
       umma_commit(BAR_S_FULL);
     }
     for (int j = 0; j < p.nkv; ++j) {
@@ -107,7 +108,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         tc_fence_after();
         const uint64_t kdesc = make_sw128_desc(sK + s1 * ATT_TILE, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
+        for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
         umma_commit(BAR_S_FULL);
       }
       mbar_wait(BAR_P_FULL, (uint32_t)j & 1u);  // P(j) in smem, O_part(j-1) consumed
@@ -116,7 +117,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       for (int k = 0; k < 8; ++k) {
         const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
         const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
-        umma_bf16(tO, pdesc, vdesc, idesc_o, (uint32_t)(k != 0));
+        umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)(k != 0));
       }
       umma_commit(BAR_O_FULL);
       umma_commit(BAR_KV_EMPTY + 8 * s);
@@ -166,7 +167,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
           for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], a_prev, __uint_as_float(v[i]));
         }
       }
-      // pass 2: P = exp2(S*log2e - m*log2e) -> bf16 -> swizzled smem
+      // pass 2: P = exp2(S*log2e - m*log2e) -> h16 -> swizzled smem
       float rowsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -180,7 +181,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
           if (c * 32 + 2 * i >= nvalid) e0 = 0.f;
           if (c * 32 + 2 * i + 1 >= nvalid) e1 = 0.f;
           rowsum += e0 + e1;
-          pk[i] = pack_bf16x2(e0, e1);
+          pk[i] = pack_h2(e0, e1, p.fmt);
         }
         const uint32_t rowbase = sP + (uint32_t)(c >> 1) * ATT_TILE + (uint32_t)r * 128u;
 #pragma unroll
@@ -211,14 +212,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     }
     if (q0 + r < p.N) {
       const float inv = 1.0f / l;
-      bf16* dst = p.out + (long long)(row0 + q0 + r) * p.D + h * 64;
+      h16* dst = p.out + (long long)(row0 + q0 + r) * p.D + h * 64;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 u;
-        u.x = pack_bf16x2(o[8 * g] * inv, o[8 * g + 1] * inv);
-        u.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        u.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        u.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+        u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv, p.fmt);
+        u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv, p.fmt);
+        u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv, p.fmt);
+        u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv, p.fmt);
         *reinterpret_cast<uint4*>(dst + 8 * g) = u;
       }
     }
@@ -233,7 +234,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   }
 }
 
-int launch_attention(const bf16* qkv, bf16* out, int B, int N, int D, cudaStream_t stream, uint32_t v_lbo,
+int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo,
                      uint32_t v_sbo) {
   DAV2_CHECK(D % 64 == 0 && N > 0 && B > 0, "attention: bad shape B=%d N=%d D=%d", B, N, D);
   CUtensorMap tm;
@@ -250,6 +251,7 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int N, int D, cudaStream
   p.nkv = (N + 127) / 128;
   p.v_lbo = v_lbo;
   p.v_sbo = v_sbo;
+  p.fmt = fmt;
   dim3 grid((N + 127) / 128, D / 64, B);
   ProfScope ps(PC_ATTN, 4.0 * B * (D / 64) * (double)N * N * 64.0, 2.0 * 4.0 * B * (double)N * D, stream);
   attention_kernel<<<grid, 192, ATT_SMEM, stream>>>(tm, p);

@@ -5,13 +5,18 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace dav2 {
 
-typedef __nv_bfloat16 bf16;
+// 16-bit tensor-core operand storage.  The numeric format is chosen at RUN TIME (per model /
+// per call): FMT_F16 = IEEE half (the reference's AMP '16-mixed' precision, configs/trainer/default.yaml:4),
+// FMT_BF16 = bfloat16.  The codes equal the UMMA a_format / b_format values for kind::f16.
+typedef uint16_t h16;
+enum { FMT_F16 = 0, FMT_BF16 = 1 };
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -125,8 +130,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], h16 x h16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -173,33 +178,50 @@ __host__ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr,
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), a/b major (bits 15/16;
-// 0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = f16, 1 = bf16), a/b major
+// (bits 15/16; 0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_h(int M, int N, int a_mn_major, int b_mn_major, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------
 // small math / packing helpers
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int fmt) {
+  if (fmt == FMT_BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_h2(uint32_t u, int fmt) {
+  if (fmt == FMT_BF16) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+  }
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// host-side scalar conversion for weight packing
+inline uint16_t f2h_host(float x, int fmt) {
+  if (fmt == FMT_BF16) {
+    __nv_bfloat16 v = __float2bfloat16_rn(x);
+    return *reinterpret_cast<uint16_t*>(&v);
+  }
+  __half v = __float2half_rn(x);
+  return *reinterpret_cast<uint16_t*>(&v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ----------------------------------------------------------------------------------------------
 // host: TMA tensor-map encoding through the driver entry point (no -lcuda link dependency)
 // ----------------------------------------------------------------------------------------------
-// 2-D row-major bf16 tensor [rows, cols] (cols contiguous, row pitch ld elements); box = 64 cols x box_rows.
+// 2-D row-major h16 tensor [rows, cols] (cols contiguous, row pitch ld elements); box = 64 cols x box_rows.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_rows);
-// 4-D NHWC bf16 tensor [B,H,W,C]; box = 64 channels x tw x th x 1 (implicit-GEMM conv A operand).
+// 4-D NHWC h16 tensor [B,H,W,C]; box = 64 channels x tw x th x 1 (implicit-GEMM conv A operand).
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                    uint32_t tw, uint32_t th);
 

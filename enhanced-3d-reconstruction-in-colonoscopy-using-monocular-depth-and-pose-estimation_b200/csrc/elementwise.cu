@@ -6,14 +6,14 @@
 namespace dav2 {
 
 // ----------------------------------------------------------------------------------------------
-// LayerNorm over the last dim (D = 128*V4, V4 <= 8), fp32 in -> bf16 out, one warp per row.
+// LayerNorm over the last dim (D = 128*V4, V4 <= 8), fp32 in -> h16 out, one warp per row.
 // rows_per_img / skip_cls: when skip_cls != 0 the first row of every image (cls token) is dropped and
 // the remaining rows are written compactly ([B, N-1, D] == NHWC patch grid) - used for the DPT taps.
 // ----------------------------------------------------------------------------------------------
 template <int V4>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, bf16* __restrict__ out,
-                                                        long long rows, int rows_per_img, int skip_cls, float eps) {
+                                                        const float* __restrict__ b, h16* __restrict__ out,
+                                                        long long rows, int rows_per_img, int skip_cls, float eps, int fmt) {
   constexpr int D = V4 * 128;
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -52,15 +52,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
       uint2 u;
-      u.x = pack_bf16x2((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
-      u.y = pack_bf16x2((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+      u.x = pack_h2((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y, fmt);
+      u.y = pack_h2((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w, fmt);
       orp[lane + 32 * i] = u;
     }
   }
 }
 
-int launch_layernorm(const float* x, const float* w, const float* b, bf16* out, long long rows, int D,
-                     int rows_per_img, int skip_cls, float eps, cudaStream_t stream) {
+int launch_layernorm(const float* x, const float* w, const float* b, h16* out, long long rows, int D,
+                     int rows_per_img, int skip_cls, float eps, int fmt, cudaStream_t stream) {
   DAV2_CHECK(D % 128 == 0 && D / 128 <= 8, "layernorm: D=%d unsupported (need multiple of 128, <= 1024)", D);
   if (rows <= 0) return 0;
   const int wpb = 8;
@@ -70,7 +70,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, bf16* out, 
   ProfScope ps(PC_LAYERNORM, 0.0, (double)rows * D * 6.0, stream);
 #define LN_CASE(V)                                                                                             \
   case V:                                                                                                      \
-    layernorm_kernel<V><<<(int)blocks, wpb * 32, 0, stream>>>(x, w, b, out, rows, rows_per_img, skip_cls, eps); \
+    layernorm_kernel<V><<<(int)blocks, wpb * 32, 0, stream>>>(x, w, b, out, rows, rows_per_img, skip_cls, eps, fmt); \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -81,17 +81,17 @@ int launch_layernorm(const float* x, const float* w, const float* b, bf16* out, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// Patch im2col for the 14x14 / stride-14 patch embedding: x fp32 NCHW [B,3,H,W] -> A bf16 [B*ph*pw, KP]
+// Patch im2col for the 14x14 / stride-14 patch embedding: x fp32 NCHW [B,3,H,W] -> A h16 [B*ph*pw, KP]
 // with k = c*196 + ky*14 + kx (the flattening of Conv2d weight [D,3,14,14]); columns 588..KP-1 are zero.
 // One thread per (patch, c, ky) segment of 14 contiguous input floats.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ A, int B,
-                                                           int H, int W, int ph, int pw, int KP) {
+__global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ x, h16* __restrict__ A, int B,
+                                                           int H, int W, int ph, int pw, int KP, int fmt) {
   const long long nseg = (long long)B * ph * pw * 43;  // 42 data segments + 1 zero-pad segment
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += (long long)gridDim.x * blockDim.x) {
     const long long patch = i / 43;
     const int seg = (int)(i - patch * 43);
-    bf16* dst = A + patch * KP;
+    h16* dst = A + patch * KP;
     if (seg == 42) {
       for (int k = 588; k < KP; k += 2) *reinterpret_cast<uint32_t*>(dst + k) = 0u;
       continue;
@@ -103,11 +103,11 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restri
     const float* src = x + (((long long)bimg * 3 + c) * H + (py * 14 + ky)) * W + px * 14;
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + seg * 14);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) d32[k] = pack_bf16x2(__ldg(src + 2 * k), __ldg(src + 2 * k + 1));
+    for (int k = 0; k < 7; ++k) d32[k] = pack_h2(__ldg(src + 2 * k), __ldg(src + 2 * k + 1), fmt);
   }
 }
 
-int launch_patch_im2col(const float* x, bf16* A, int B, int H, int W, int KP, cudaStream_t stream) {
+int launch_patch_im2col(const float* x, h16* A, int B, int H, int W, int KP, int fmt, cudaStream_t stream) {
   DAV2_CHECK(H % 14 == 0 && W % 14 == 0 && KP >= 588 && KP % 64 == 0, "patch_im2col: bad shape H=%d W=%d KP=%d", H, W, KP);
   const int ph = H / 14, pw = W / 14;
   const long long nseg = (long long)B * ph * pw * 43;
@@ -115,7 +115,7 @@ int launch_patch_im2col(const float* x, bf16* A, int B, int H, int W, int KP, cu
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   ProfScope ps(PC_IM2COL, 0.0, (double)B * 3 * H * W * 4.0 + (double)B * ph * pw * KP * 2.0, stream);
-  patch_im2col_kernel<<<(int)blocks, 256, 0, stream>>>(x, A, B, H, W, ph, pw, KP);
+  patch_im2col_kernel<<<(int)blocks, 256, 0, stream>>>(x, A, B, H, W, ph, pw, KP, fmt);
   DAV2_LAUNCH_OK();
   return 0;
 }
@@ -137,10 +137,10 @@ int launch_cls_row(float* x, const float* cls, const float* pos, int B, int ntok
 }
 
 // ----------------------------------------------------------------------------------------------
-// im2col for Conv2d(k=3, stride=2, pad=1) on NHWC bf16: [B,H,W,C] -> [B*Ho*Wo, 9*C], k = tap*C + c.
+// im2col for Conv2d(k=3, stride=2, pad=1) on NHWC h16: [B,H,W,C] -> [B*Ho*Wo, 9*C], k = tap*C + c.
 // One thread per 8-channel (16 B) vector.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__ in, bf16* __restrict__ A, int B, int H,
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const h16* __restrict__ in, h16* __restrict__ A, int B, int H,
                                                         int W, int C, int Ho, int Wo) {
   const int c8 = C / 8;
   const long long total = (long long)B * Ho * Wo * 9 * c8;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__
   }
 }
 
-int launch_im2col_s2(const bf16* in, bf16* A, int B, int H, int W, int C, cudaStream_t stream) {
+int launch_im2col_s2(const h16* in, h16* A, int B, int H, int W, int C, cudaStream_t stream) {
   DAV2_CHECK(C % 8 == 0, "im2col_s2: C=%d must be a multiple of 8", C);
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)B * Ho * Wo * 9 * (C / 8);
@@ -175,11 +175,11 @@ int launch_im2col_s2(const bf16* in, bf16* A, int B, int H, int W, int C, cudaSt
 }
 
 // ----------------------------------------------------------------------------------------------
-// Bilinear resize, align_corners=True, NHWC bf16 -> NHWC bf16 (fp32 blend), 8 channels per thread.
+// Bilinear resize, align_corners=True, NHWC h16 -> NHWC h16 (fp32 blend), 8 channels per thread.
 // src coordinate = dst * (in-1)/(out-1), exactly like F.interpolate(..., align_corners=True).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B,
-                                                            int Hi, int Wi, int Ho, int Wo, int C, float sy, float sx) {
+__global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restrict__ in, h16* __restrict__ out, int B,
+                                                            int Hi, int Wi, int Ho, int Wo, int C, float sy, float sx, int fmt) {
   const int c8 = C / 8;
   const long long total = (long long)B * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const bf16* __restri
     x0 = min(x0, Wi - 1);
     const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
     const float wy = fy - (float)y0, wx = fx - (float)x0;
-    const bf16* base = in + (long long)b * Hi * Wi * C;
+    const h16* base = in + (long long)b * Hi * Wi * C;
     const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
     const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
     const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
@@ -209,15 +209,15 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const bf16* __restri
     const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 fa = unpack_bf16x2(a[k]), fb = unpack_bf16x2(bq[k]), fc = unpack_bf16x2(c[k]), fd = unpack_bf16x2(d[k]);
-      ow[k] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                          w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+      const float2 fa = unpack_h2(a[k], fmt), fb = unpack_h2(bq[k], fmt), fc = unpack_h2(c[k], fmt), fd = unpack_h2(d[k], fmt);
+      ow[k] = pack_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                      w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, fmt);
     }
     reinterpret_cast<uint4*>(out)[i] = o;
   }
 }
 
-int launch_bilinear_nhwc(const bf16* in, bf16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t stream) {
+int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int fmt, cudaStream_t stream) {
   DAV2_CHECK(C % 8 == 0, "bilinear: C=%d must be a multiple of 8", C);
   const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
@@ -226,7 +226,7 @@ int launch_bilinear_nhwc(const bf16* in, bf16* out, int B, int Hi, int Wi, int H
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   ProfScope ps(PC_RESAMPLE, 0.0, 2.0 * C * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
-  bilinear_nhwc_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, C, sy, sx);
+  bilinear_nhwc_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, C, sy, sx, fmt);
   DAV2_LAUNCH_OK();
   return 0;
 }
@@ -261,20 +261,6 @@ int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int 
   if (blocks < 1) return 0;
   ProfScope ps(PC_RESAMPLE, 0.0, 4.0 * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
   bilinear_f32_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, sy, sx);
-  DAV2_LAUNCH_OK();
-  return 0;
-}
-
-// fp32 -> bf16 cast (weights packing helper)
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(in[i]);
-}
-int launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream) {
-  if (n <= 0) return 0;
-  long long blocks = (n + 255) / 256;
-  if (blocks > 4096) blocks = 4096;
-  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, n);
   DAV2_LAUNCH_OK();
   return 0;
 }

@@ -4,17 +4,17 @@
 
 namespace dav2 {
 
-int launch_layernorm(const float* x, const float* w, const float* b, bf16* out, long long rows, int D,
-                     int rows_per_img, int skip_cls, float eps, cudaStream_t stream);
-int launch_patch_im2col(const float* x, bf16* A, int B, int H, int W, int KP, cudaStream_t stream);
+int launch_layernorm(const float* x, const float* w, const float* b, h16* out, long long rows, int D,
+                     int rows_per_img, int skip_cls, float eps, int fmt, cudaStream_t stream);
+int launch_patch_im2col(const float* x, h16* A, int B, int H, int W, int KP, int fmt, cudaStream_t stream);
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int ntok, int D, cudaStream_t stream);
-int launch_im2col_s2(const bf16* in, bf16* A, int B, int H, int W, int C, cudaStream_t stream);
-int launch_bilinear_nhwc(const bf16* in, bf16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t stream);
+int launch_im2col_s2(const h16* in, h16* A, int B, int H, int W, int C, cudaStream_t stream);
+int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int fmt, cudaStream_t stream);
 int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
-int launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
+int launch_cast_bf16(const float* in, h16* out, long long n, cudaStream_t stream);
 
 // attention.cu
-int launch_attention(const bf16* qkv, bf16* out, int B, int N, int D, cudaStream_t stream, uint32_t v_lbo = 1024,
+int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo = 1024,
                      uint32_t v_sbo = 1024);
 
 // geometry.cu

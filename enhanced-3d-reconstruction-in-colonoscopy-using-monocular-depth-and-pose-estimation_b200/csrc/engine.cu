@@ -33,33 +33,33 @@ static int upload_f32(const float* data, int64_t n, float** out) {
   return dev_upload(data, (size_t)n * 4, reinterpret_cast<void**>(out));
 }
 
-static int upload_bf16(const std::vector<bf16>& v, bf16** out) {
+static int upload_h(const std::vector<h16>& v, h16** out) {
   return dev_upload(v.data(), v.size() * 2, reinterpret_cast<void**>(out));
 }
 
-static std::vector<bf16> to_bf16(const float* d, int64_t n, float scale_first = 1.f, int64_t first = 0) {
-  std::vector<bf16> v((size_t)n);
-  for (int64_t i = 0; i < n; ++i) v[(size_t)i] = __float2bfloat16_rn(i < first ? d[i] * scale_first : d[i]);
+static std::vector<h16> to_h(int fmt, const float* d, int64_t n, float scale_first = 1.f, int64_t first = 0) {
+  std::vector<h16> v((size_t)n);
+  for (int64_t i = 0; i < n; ++i) v[(size_t)i] = f2h_host(i < first ? d[i] * scale_first : d[i], fmt);
   return v;
 }
 
 // Conv2d weight [Cout, Cin, 3, 3] -> [Cout][tap*Cpad + c] (tap = ky*3+kx), zero padded to Cpad
-static std::vector<bf16> pack_conv3x3(const float* w, int Cout, int Cin, int Cpad) {
-  std::vector<bf16> v((size_t)Cout * 9 * Cpad, __float2bfloat16_rn(0.f));
+static std::vector<h16> pack_conv3x3(int fmt, const float* w, int Cout, int Cin, int Cpad) {
+  std::vector<h16> v((size_t)Cout * 9 * Cpad, f2h_host(0.f, fmt));
   for (int n = 0; n < Cout; ++n)
     for (int c = 0; c < Cin; ++c)
       for (int t = 0; t < 9; ++t)
-        v[((size_t)n * 9 + t) * Cpad + c] = __float2bfloat16_rn(w[((size_t)n * Cin + c) * 9 + t]);
+        v[((size_t)n * 9 + t) * Cpad + c] = f2h_host(w[((size_t)n * Cin + c) * 9 + t], fmt);
   return v;
 }
 
 // ConvTranspose2d weight [Cin, Cout, s, s] -> [(ky*s+kx)*Cout + co][ci]
-static std::vector<bf16> pack_convT(const float* w, int Cin, int Cout, int s) {
-  std::vector<bf16> v((size_t)s * s * Cout * Cin);
+static std::vector<h16> pack_convT(int fmt, const float* w, int Cin, int Cout, int s) {
+  std::vector<h16> v((size_t)s * s * Cout * Cin);
   for (int ci = 0; ci < Cin; ++ci)
     for (int co = 0; co < Cout; ++co)
       for (int k = 0; k < s * s; ++k)
-        v[((size_t)k * Cout + co) * Cin + ci] = __float2bfloat16_rn(w[((size_t)ci * Cout + co) * s * s + k]);
+        v[((size_t)k * Cout + co) * Cin + ci] = f2h_host(w[((size_t)ci * Cout + co) * s * s + k], fmt);
   return v;
 }
 
@@ -82,6 +82,7 @@ Model::Model(const dav2_config& c) : cfg(c) {
   L = c.depth;
   heads = c.num_heads;
   F = c.features;
+  fmt = c.precision == 1 ? FMT_BF16 : FMT_F16;
   blk.resize(L);
   memset(blk.data(), 0, sizeof(BlockW) * L);
   memset(proj_w, 0, sizeof(proj_w)); memset(proj_b, 0, sizeof(proj_b));
@@ -143,10 +144,10 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
     owned.push_back(_p);                                  \
     dst = _p;                                             \
   } while (0)
-#define STORE_BF16(dst, vec)                              \
+#define STORE_H16(dst, vec)                              \
   do {                                                    \
-    bf16* _p = nullptr;                                   \
-    if (int rc = upload_bf16(vec, &_p)) return rc;        \
+    h16* _p = nullptr;                                   \
+    if (int rc = upload_h(vec, &_p)) return rc;        \
     owned.push_back(_p);                                  \
     dst = _p;                                             \
   } while (0)
@@ -161,10 +162,10 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
     STORE_F32(pos);
   } else if (K == "pretrained.patch_embed.proj.weight") {
     WANT_SHAPE(Dl, 3, 14, 14);
-    std::vector<bf16> v((size_t)D * KP_PATCH, __float2bfloat16_rn(0.f));
+    std::vector<h16> v((size_t)D * KP_PATCH, f2h_host(0.f, fmt));
     for (int d = 0; d < D; ++d)
-      for (int k = 0; k < 588; ++k) v[(size_t)d * KP_PATCH + k] = __float2bfloat16_rn(data[(size_t)d * 588 + k]);
-    STORE_BF16(patch_w, v);
+      for (int k = 0; k < 588; ++k) v[(size_t)d * KP_PATCH + k] = f2h_host(data[(size_t)d * 588 + k], fmt);
+    STORE_H16(patch_w, v);
   } else if (K == "pretrained.patch_embed.proj.bias") {
     WANT_SHAPE(Dl);
     STORE_F32(patch_b);
@@ -186,8 +187,8 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
     else if (T == "ls2.gamma") { WANT_SHAPE(Dl); STORE_F32(b.ls2); }
     else if (T == "attn.qkv.weight") {
       WANT_SHAPE(3 * Dl, Dl);
-      // q rows pre-scaled by d_head^-1/2 = 1/8 (exact in bf16/fp32): upstream scales q before q@k^T
-      STORE_BF16(b.qkv_w, to_bf16(data, n, 0.125f, Dl * Dl));
+      // q rows pre-scaled by d_head^-1/2 = 1/8 (exact in h16/fp32): upstream scales q before q@k^T
+      STORE_H16(b.qkv_w, to_h(fmt, data, n, 0.125f, Dl * Dl));
     } else if (T == "attn.qkv.bias") {
       WANT_SHAPE(3 * Dl);
       std::vector<float> t(data, data + n);
@@ -197,53 +198,53 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
       owned.push_back(p);
       b.qkv_b = p;
     }
-    else if (T == "attn.proj.weight") { WANT_SHAPE(Dl, Dl); STORE_BF16(b.proj_w, to_bf16(data, n)); }
+    else if (T == "attn.proj.weight") { WANT_SHAPE(Dl, Dl); STORE_H16(b.proj_w, to_h(fmt, data, n)); }
     else if (T == "attn.proj.bias") { WANT_SHAPE(Dl); STORE_F32(b.proj_b); }
-    else if (T == "mlp.fc1.weight") { WANT_SHAPE(4 * Dl, Dl); STORE_BF16(b.fc1_w, to_bf16(data, n)); }
+    else if (T == "mlp.fc1.weight") { WANT_SHAPE(4 * Dl, Dl); STORE_H16(b.fc1_w, to_h(fmt, data, n)); }
     else if (T == "mlp.fc1.bias") { WANT_SHAPE(4 * Dl); STORE_F32(b.fc1_b); }
-    else if (T == "mlp.fc2.weight") { WANT_SHAPE(Dl, 4 * Dl); STORE_BF16(b.fc2_w, to_bf16(data, n)); }
+    else if (T == "mlp.fc2.weight") { WANT_SHAPE(Dl, 4 * Dl); STORE_H16(b.fc2_w, to_h(fmt, data, n)); }
     else if (T == "mlp.fc2.bias") { WANT_SHAPE(Dl); STORE_F32(b.fc2_b); }
     else { set_last_error("set_weight: unknown key %s", key); return -4; }
   } else if (sscanf(key, "depth_head.projects.%d.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 0 && idx < 4, "set_weight(%s): index", key);
     const int64_t oc = cfg.out_channels[idx];
-    if (!strcmp(tail, "weight")) { WANT_SHAPE(oc, Dl, 1, 1); STORE_BF16(proj_w[idx], to_bf16(data, n)); }
+    if (!strcmp(tail, "weight")) { WANT_SHAPE(oc, Dl, 1, 1); STORE_H16(proj_w[idx], to_h(fmt, data, n)); }
     else { WANT_SHAPE(oc); STORE_F32(proj_b[idx]); }
   } else if (sscanf(key, "depth_head.resize_layers.%d.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx == 0 || idx == 1 || idx == 3, "set_weight(%s): index", key);
     const int64_t oc = cfg.out_channels[idx];
     if (!strcmp(tail, "bias")) { WANT_SHAPE(oc); STORE_F32(rs_b[idx]); }
-    else if (idx == 3) { WANT_SHAPE(oc, oc, 3, 3); STORE_BF16(rs_w[3], pack_conv3x3(data, (int)oc, (int)oc, (int)oc)); }
+    else if (idx == 3) { WANT_SHAPE(oc, oc, 3, 3); STORE_H16(rs_w[3], pack_conv3x3(fmt, data, (int)oc, (int)oc, (int)oc)); }
     else {
       const int s = idx == 0 ? 4 : 2;
       WANT_SHAPE(oc, oc, s, s);
-      STORE_BF16(rs_w[idx], pack_convT(data, (int)oc, (int)oc, s));
+      STORE_H16(rs_w[idx], pack_convT(fmt, data, (int)oc, (int)oc, s));
     }
   } else if (sscanf(key, "depth_head.scratch.layer%d_rn.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 1 && idx <= 4 && !strcmp(tail, "weight"), "set_weight(%s): bad key", key);
     const int64_t oc = cfg.out_channels[idx - 1];
     WANT_SHAPE(F, oc, 3, 3);
-    STORE_BF16(rn_w[idx - 1], pack_conv3x3(data, F, (int)oc, (int)((oc + 63) / 64 * 64)));
+    STORE_H16(rn_w[idx - 1], pack_conv3x3(fmt, data, F, (int)oc, (int)((oc + 63) / 64 * 64)));
   } else if (sscanf(key, "depth_head.scratch.refinenet%d.resConfUnit%d.conv%d.%63s", &idx, &u, &c, tail) == 4) {
     DAV2_CHECK(idx >= 1 && idx <= 4 && u >= 1 && u <= 2 && c >= 1 && c <= 2, "set_weight(%s): bad key", key);
     Fusion& f = ref[idx - 1];
     if (!strcmp(tail, "weight")) {
       WANT_SHAPE(F, F, 3, 3);
-      STORE_BF16(f.rcu_w[u - 1][c - 1], pack_conv3x3(data, F, F, (F + 63) / 64 * 64));
+      STORE_H16(f.rcu_w[u - 1][c - 1], pack_conv3x3(fmt, data, F, F, (F + 63) / 64 * 64));
     } else { WANT_SHAPE(F); STORE_F32(f.rcu_b[u - 1][c - 1]); }
   } else if (sscanf(key, "depth_head.scratch.refinenet%d.out_conv.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 1 && idx <= 4, "set_weight(%s): bad key", key);
-    if (!strcmp(tail, "weight")) { WANT_SHAPE(F, F, 1, 1); STORE_BF16(ref[idx - 1].out_w, to_bf16(data, n)); }
+    if (!strcmp(tail, "weight")) { WANT_SHAPE(F, F, 1, 1); STORE_H16(ref[idx - 1].out_w, to_h(fmt, data, n)); }
     else { WANT_SHAPE(F); STORE_F32(ref[idx - 1].out_b); }
   } else if (K == "depth_head.scratch.output_conv1.weight") {
     WANT_SHAPE(F / 2, F, 3, 3);
-    STORE_BF16(oc1_w, pack_conv3x3(data, F / 2, F, (F + 63) / 64 * 64));
+    STORE_H16(oc1_w, pack_conv3x3(fmt, data, F / 2, F, (F + 63) / 64 * 64));
   } else if (K == "depth_head.scratch.output_conv1.bias") {
     WANT_SHAPE(F / 2);
     STORE_F32(oc1_b);
   } else if (K == "depth_head.scratch.output_conv2.0.weight") {
     WANT_SHAPE(32, F / 2, 3, 3);
-    STORE_BF16(oc2_w, pack_conv3x3(data, 32, F / 2, (F / 2 + 63) / 64 * 64));
+    STORE_H16(oc2_w, pack_conv3x3(fmt, data, 32, F / 2, (F / 2 + 63) / 64 * 64));
   } else if (K == "depth_head.scratch.output_conv2.0.bias") {
     WANT_SHAPE(32);
     STORE_F32(oc2_b);
@@ -260,7 +261,7 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
   loaded.insert(K);
   return 0;
 #undef STORE_F32
-#undef STORE_BF16
+#undef STORE_H16
 }
 
 bool Model::weights_complete(std::string* missing) const {
@@ -299,13 +300,14 @@ int Model::buf(const char* name, size_t bytes, void** out) {
 // ----------------------------------------------------------------------------------------------
 // GEMM / conv wrappers
 // ----------------------------------------------------------------------------------------------
-static GemmParams blank_params() {
+static GemmParams blank_params(int fmt) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.fmt = fmt;
   return p;
 }
 
-int gemm_linear(int mode, const bf16* A, int M, int K, long long lda, const bf16* Wt, int N, GemmParams p,
+int gemm_linear(int mode, const h16* A, int M, int K, long long lda, const h16* Wt, int N, GemmParams p,
                 cudaStream_t stream) {
   DAV2_CHECK(N % 4 == 0, "gemm: N=%d must be a multiple of 4", N);
   const int bn = pick_bn(N);
@@ -334,7 +336,7 @@ static void pick_conv_tile(int H, int W, int* tw, int* th) {
   }
 }
 
-int conv3x3(int mode, const bf16* in, int B, int H, int W, int Cin, const bf16* Wp, int Cout, GemmParams p,
+int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp, int Cout, GemmParams p,
             cudaStream_t stream) {
   DAV2_CHECK(Cout % 4 == 0 && Cin % 8 == 0, "conv3x3: Cin=%d Cout=%d unsupported", Cin, Cout);
   const int bn = mode == GM_CONV_HEAD ? 32 : pick_bn(Cout);
@@ -380,9 +382,9 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
     DAV2_CHECK(it != pos_tables.end(), "forward: no position table for a %dx%d patch grid (call dav2_set_pos_embed)", ph, pw);
     posT = it->second;
   }
-  const size_t S2 = sizeof(bf16);
+  const size_t S2 = sizeof(h16);
 
-  bf16 *patchA, *XN, *QKV, *ATT, *HID, *TAP[4];
+  h16 *patchA, *XN, *QKV, *ATT, *HID, *TAP[4];
   float* X;
   RC(buf("patch_A", (size_t)MP * KP_PATCH * S2, (void**)&patchA));
   RC(buf("x", (size_t)M * D * 4, (void**)&X));
@@ -397,9 +399,9 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   }
 
   // ---- patch embed + cls + pos ------------------------------------------------------------
-  RC(launch_patch_im2col(x, patchA, B, H, W, KP_PATCH, stream));
+  RC(launch_patch_im2col(x, patchA, B, H, W, KP_PATCH, fmt, stream));
   {
-    GemmParams p = blank_params();
+    GemmParams p = blank_params(fmt);
     p.out = X; p.ldo = D; p.bias = patch_b; p.pos = posT; p.P = P;
     RC(gemm_linear(GM_PATCH, patchA, MP, KP_PATCH, KP_PATCH, patch_w, D, p, stream));
   }
@@ -409,32 +411,32 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   int next_tap = 0;
   for (int l = 0; l < L; ++l) {
     const BlockW& w = blk[l];
-    RC(launch_layernorm(X, w.n1w, w.n1b, XN, M, D, N, 0, 1e-6f, stream));
+    RC(launch_layernorm(X, w.n1w, w.n1b, XN, M, D, N, 0, 1e-6f, fmt, stream));
     {
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = QKV; p.ldo = 3 * D; p.bias = w.qkv_b;
       RC(gemm_linear(GM_LINEAR_BF16, XN, M, D, D, w.qkv_w, 3 * D, p, stream));
     }
-    RC(launch_attention(QKV, ATT, B, N, D, stream));
+    RC(launch_attention(QKV, ATT, B, N, D, fmt, stream));
     {
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = X; p.ldo = D; p.bias = w.proj_b; p.gamma = w.ls1;
       RC(gemm_linear(GM_LINEAR_RESID, ATT, M, D, D, w.proj_w, D, p, stream));
     }
-    RC(launch_layernorm(X, w.n2w, w.n2b, XN, M, D, N, 0, 1e-6f, stream));
+    RC(launch_layernorm(X, w.n2w, w.n2b, XN, M, D, N, 0, 1e-6f, fmt, stream));
     {
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = HID; p.ldo = 4 * D; p.bias = w.fc1_b; p.act = 1;
       RC(gemm_linear(GM_LINEAR_BF16, XN, M, D, D, w.fc1_w, 4 * D, p, stream));
     }
     {
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = X; p.ldo = D; p.bias = w.fc2_b; p.gamma = w.ls2;
       RC(gemm_linear(GM_LINEAR_RESID, HID, M, 4 * D, 4 * D, w.fc2_w, D, p, stream));
     }
     if (next_tap < 4 && l == cfg.tap_layers[next_tap]) {
       // final norm on the tap, cls dropped, written as the NHWC patch grid [B, ph, pw, D]
-      RC(launch_layernorm(X, norm_w, norm_b, TAP[next_tap], M, D, N, 1, 1e-6f, stream));
+      RC(launch_layernorm(X, norm_w, norm_b, TAP[next_tap], M, D, N, 1, 1e-6f, fmt, stream));
       ++next_tap;
     }
   }
@@ -444,14 +446,14 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   const int* oc = cfg.out_channels;
   const int hh[4] = {4 * ph, 2 * ph, ph, (ph + 1) / 2};
   const int ww[4] = {4 * pw, 2 * pw, pw, (pw + 1) / 2};
-  bf16* lvl[4];
+  h16* lvl[4];
   // reassemble: 1x1 projection (+ resize)
   for (int i = 0; i < 4; ++i) {
     char nm[24];
-    bf16* pr;
+    h16* pr;
     snprintf(nm, sizeof(nm), "proj%d", i);
     RC(buf(nm, (size_t)MP * oc[i] * S2, (void**)&pr));
-    GemmParams p = blank_params();
+    GemmParams p = blank_params(fmt);
     p.out = pr; p.ldo = oc[i]; p.bias = proj_b[i];
     RC(gemm_linear(GM_LINEAR_BF16, TAP[i], MP, D, D, proj_w[i], oc[i], p, stream));
     if (i == 2) {
@@ -460,51 +462,51 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
       const int s = i == 0 ? 4 : 2;
       snprintf(nm, sizeof(nm), "lvl%d", i);
       RC(buf(nm, (size_t)B * hh[i] * ww[i] * oc[i] * S2, (void**)&lvl[i]));
-      GemmParams q = blank_params();
+      GemmParams q = blank_params(fmt);
       q.out = lvl[i]; q.bias = rs_b[i]; q.convt_s = s; q.convt_cout = oc[i]; q.H = ph; q.W = pw;
       RC(gemm_linear(GM_CONVT, pr, MP, oc[i], oc[i], rs_w[i], s * s * oc[i], q, stream));
     } else {
-      bf16* col;
+      h16* col;
       RC(buf("lvl3_im2col", (size_t)B * hh[3] * ww[3] * 9 * oc[3] * S2, (void**)&col));
       RC(buf("lvl3", (size_t)B * hh[3] * ww[3] * oc[3] * S2, (void**)&lvl[3]));
       RC(launch_im2col_s2(pr, col, B, ph, pw, oc[3], stream));
-      GemmParams q = blank_params();
+      GemmParams q = blank_params(fmt);
       q.out = lvl[3]; q.ldo = oc[3]; q.bias = rs_b[3];
       RC(gemm_linear(GM_LINEAR_BF16, col, B * hh[3] * ww[3], 9 * oc[3], 9 * oc[3], rs_w[3], oc[3], q, stream));
     }
   }
   // layer_rn 3x3 (no bias): keep x and relu(x)
-  bf16 *rn[4], *rnr[4];
+  h16 *rn[4], *rnr[4];
   for (int i = 0; i < 4; ++i) {
     char nm[24];
     snprintf(nm, sizeof(nm), "rn%d", i);
     RC(buf(nm, (size_t)B * hh[i] * ww[i] * F * S2, (void**)&rn[i]));
     snprintf(nm, sizeof(nm), "rn%d_relu", i);
     RC(buf(nm, (size_t)B * hh[i] * ww[i] * F * S2, (void**)&rnr[i]));
-    GemmParams p = blank_params();
+    GemmParams p = blank_params(fmt);
     p.out = rn[i]; p.out_relu = rnr[i];
     RC(conv3x3(GM_CONV_BF16, lvl[i], B, hh[i], ww[i], oc[i], rn_w[i], F, p, stream));
   }
   // fusion blocks (refinenet4 -> refinenet1).  out_conv (1x1) commutes with the bilinear resize
   // (both linear, bilinear weights sum to 1), so it runs at the LOW resolution: 4x fewer FLOPs.
   const size_t big = (size_t)B * hh[0] * ww[0] * F * S2;
-  bf16 *T, *S, *SR, *Y, *OCb;
+  h16 *T, *S, *SR, *Y, *OCb;
   RC(buf("scratch_t", big, (void**)&T));
   RC(buf("scratch_s", big, (void**)&S));
   RC(buf("scratch_sr", big, (void**)&SR));
   RC(buf("scratch_y", big, (void**)&Y));
   RC(buf("scratch_oc", big, (void**)&OCb));
-  bf16* up_prev = nullptr;
+  h16* up_prev = nullptr;
   for (int i = 3; i >= 0; --i) {
     const Fusion& f = ref[i];
     const int h = hh[i], w = ww[i];
-    const bf16 *in = rn[i], *in_relu = rnr[i];
+    const h16 *in = rn[i], *in_relu = rnr[i];
     if (up_prev) {
       // S = resConfUnit1(rn) + up_prev ; SR = relu(S)
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = T; p.bias = f.rcu_b[0][0]; p.act = 2;
       RC(conv3x3(GM_CONV_BF16, in_relu, B, h, w, F, f.rcu_w[0][0], F, p, stream));
-      GemmParams q = blank_params();
+      GemmParams q = blank_params(fmt);
       q.out = S; q.out_relu = SR; q.bias = f.rcu_b[0][1]; q.add1 = in; q.add2 = up_prev;
       RC(conv3x3(GM_CONV_BF16, T, B, h, w, F, f.rcu_w[0][1], F, q, stream));
       in = S;
@@ -512,39 +514,39 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
     }
     {
       // Y = resConfUnit2(in)
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = T; p.bias = f.rcu_b[1][0]; p.act = 2;
       RC(conv3x3(GM_CONV_BF16, in_relu, B, h, w, F, f.rcu_w[1][0], F, p, stream));
-      GemmParams q = blank_params();
+      GemmParams q = blank_params(fmt);
       q.out = Y; q.bias = f.rcu_b[1][1]; q.add1 = in;
       RC(conv3x3(GM_CONV_BF16, T, B, h, w, F, f.rcu_w[1][1], F, q, stream));
     }
     {
-      GemmParams p = blank_params();
+      GemmParams p = blank_params(fmt);
       p.out = OCb; p.ldo = F; p.bias = f.out_b;
       RC(gemm_linear(GM_LINEAR_BF16, Y, B * h * w, F, F, f.out_w, F, p, stream));
     }
     const int ho = i > 0 ? hh[i - 1] : 2 * hh[0], wo = i > 0 ? ww[i - 1] : 2 * ww[0];
     char nm[24];
     snprintf(nm, sizeof(nm), "path%d", i + 1);
-    bf16* up;
+    h16* up;
     RC(buf(nm, (size_t)B * ho * wo * F * S2, (void**)&up));
-    RC(launch_bilinear_nhwc(OCb, up, B, h, w, ho, wo, F, stream));
+    RC(launch_bilinear_nhwc(OCb, up, B, h, w, ho, wo, F, fmt, stream));
     up_prev = up;
   }
   // head: output_conv1 -> bilinear to (H, W) -> 3x3 + ReLU + 1x1 + sigmoid * max_depth
   const int h8 = 2 * hh[0], w8 = 2 * ww[0];
-  bf16 *O1, *O1U;
+  h16 *O1, *O1U;
   RC(buf("out1", (size_t)B * h8 * w8 * (F / 2) * S2, (void**)&O1));
   RC(buf("out1_up", (size_t)B * H * W * (F / 2) * S2, (void**)&O1U));
   {
-    GemmParams p = blank_params();
+    GemmParams p = blank_params(fmt);
     p.out = O1; p.bias = oc1_b;
     RC(conv3x3(GM_CONV_BF16, up_prev, B, h8, w8, F, oc1_w, F / 2, p, stream));
   }
-  RC(launch_bilinear_nhwc(O1, O1U, B, h8, w8, H, W, F / 2, stream));
+  RC(launch_bilinear_nhwc(O1, O1U, B, h8, w8, H, W, F / 2, fmt, stream));
   {
-    GemmParams p = blank_params();
+    GemmParams p = blank_params(fmt);
     p.out = depth; p.bias = oc2_b; p.head_w = oc3_w; p.head_b = oc3_b; p.max_depth = cfg.max_depth;
     RC(conv3x3(GM_CONV_HEAD, O1U, B, H, W, F / 2, oc2_w, 32, p, stream));
   }

@@ -15,12 +15,12 @@ namespace dav2 {
 
 struct BlockW {
   float *n1w, *n1b, *n2w, *n2b, *qkv_b, *proj_b, *fc1_b, *fc2_b, *ls1, *ls2;
-  bf16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+  h16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
 };
 struct Fusion {
-  bf16* out_w;
+  h16* out_w;
   float* out_b;
-  bf16* rcu_w[2][2];   // [resConfUnit 1|2][conv 1|2], tap-major packed
+  h16* rcu_w[2][2];   // [resConfUnit 1|2][conv 1|2], tap-major packed
   float* rcu_b[2][2];
 };
 struct DevBuf {
@@ -31,18 +31,19 @@ struct DevBuf {
 struct Model {
   dav2_config cfg;
   int D, L, heads, F;
+  int fmt;  // FMT_F16 (default; the reference's AMP precision) or FMT_BF16
   // encoder
-  bf16* patch_w = nullptr;
+  h16* patch_w = nullptr;
   float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr;
   std::vector<BlockW> blk;
   // DPT head
-  bf16* proj_w[4];
+  h16* proj_w[4];
   float* proj_b[4];
-  bf16* rs_w[4];
+  h16* rs_w[4];
   float* rs_b[4];
-  bf16* rn_w[4];
+  h16* rn_w[4];
   Fusion ref[4];  // refinenet1..4
-  bf16 *oc1_w = nullptr, *oc2_w = nullptr;
+  h16 *oc1_w = nullptr, *oc2_w = nullptr;
   float *oc1_b = nullptr, *oc2_b = nullptr, *oc3_w = nullptr;
   float oc3_b = 0.f;
 
@@ -62,9 +63,9 @@ struct Model {
   int debug_read(const char* name, void* dst, int64_t bytes, cudaStream_t stream);
 };
 
-int gemm_linear(int mode, const bf16* A, int M, int K, long long lda, const bf16* Wt, int N, GemmParams p,
+int gemm_linear(int mode, const h16* A, int M, int K, long long lda, const h16* Wt, int N, GemmParams p,
                 cudaStream_t stream);
-int conv3x3(int mode, const bf16* in, int B, int H, int W, int Cin, const bf16* Wp, int Cout, GemmParams p,
+int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp, int Cout, GemmParams p,
             cudaStream_t stream);
 
 }  // namespace dav2

@@ -1,6 +1,6 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T      bf16 operands (K-major, 128B-swizzled smem tiles fed by TMA),
+//   D[M,N] = A[M,K] * B[N,K]^T      h16 operands (K-major, 128B-swizzled smem tiles fed by TMA),
 //                                   fp32 accumulators in TMEM (double buffered), fused epilogues.
 //
 // Roles (192 threads, 1 CTA / SM, grid = min(tiles, #SM), static round-robin tile schedule):
@@ -20,11 +20,11 @@
 namespace dav2 {
 
 enum GemmMode {
-  GM_LINEAR_BF16 = 0,  // out bf16 = act(acc+bias) [+add1][+add2]; optional second output relu(out)
+  GM_LINEAR_BF16 = 0,  // out h16 = act(acc+bias) [+add1][+add2]; optional second output relu(out)
   GM_LINEAR_RESID = 1, // x(fp32) += gamma * (acc + bias)               (LayerScale + residual)
   GM_PATCH = 2,        // x(fp32)[b, 1+p, :] = acc + bias + pos[1+p, :]   (patch embed + pos embed)
-  GM_CONVT = 3,        // ConvTranspose2d(k = s): bf16 scatter to (s*y+ky, s*x+kx), bias per out channel
-  GM_CONV_BF16 = 4,    // 3x3 pad-1 conv, NHWC bf16 out, same epilogue options as GM_LINEAR_BF16
+  GM_CONVT = 3,        // ConvTranspose2d(k = s): h16 scatter to (s*y+ky, s*x+kx), bias per out channel
+  GM_CONV_BF16 = 4,    // 3x3 pad-1 conv, NHWC h16 out, same epilogue options as GM_LINEAR_BF16
   GM_CONV_HEAD = 5,    // 3x3 conv (N=32) + ReLU + 1x1 (32->1) + sigmoid * max_depth -> fp32 depth
 };
 
@@ -37,14 +37,15 @@ struct GemmParams {
   // epilogue
   void* out;
   long long ldo;
-  bf16* out_relu;
+  h16* out_relu;
   const float* bias;
   const float* gamma;
-  const bf16* add1;
-  const bf16* add2;
+  const h16* add1;
+  const h16* add2;
   const float* pos;
   int P;                 // patches per image (GM_PATCH)
   int act;               // 0 none, 1 GELU(erf), 2 ReLU
+  int fmt;               // FMT_F16 / FMT_BF16: operand + 16-bit output format
   int convt_s, convt_cout;
   const float* head_w;   // [32]
   float head_b, max_depth;
@@ -152,7 +153,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (threadIdx.x == 32) {
     // ================================ MMA issuer ============================================
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t idesc = make_idesc_h(128, BN, 0, 0, p.fmt);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -169,7 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_h16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
         umma_commit(EMPTY_BAR(stage));
         if (++stage == STAGES) {
           stage = 0;
@@ -300,22 +301,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
               if (p.add1) {
                 const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.add1 + off));
-                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+                const float2 f0 = unpack_h2(u.x, p.fmt), f1 = unpack_h2(u.y, p.fmt);
                 a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
               }
               if (p.add2) {
                 const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.add2 + off));
-                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+                const float2 f0 = unpack_h2(u.x, p.fmt), f1 = unpack_h2(u.y, p.fmt);
                 a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
               }
               uint2 o;
-              o.x = pack_bf16x2(a.x, a.y);
-              o.y = pack_bf16x2(a.z, a.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
+              o.x = pack_h2(a.x, a.y, p.fmt);
+              o.y = pack_h2(a.z, a.w, p.fmt);
+              *reinterpret_cast<uint2*>(reinterpret_cast<h16*>(p.out) + off) = o;
               if (p.out_relu) {
                 uint2 orl;
-                orl.x = pack_bf16x2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
-                orl.y = pack_bf16x2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+                orl.x = pack_h2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), p.fmt);
+                orl.y = pack_h2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f), p.fmt);
                 *reinterpret_cast<uint2*>(p.out_relu + off) = orl;
               }
             }

@@ -4,7 +4,9 @@ reference imports (run.py:44, lightning_model.py:16, depth_to_pointcloud_dav2.py
 ``DepthAnythingV2`` keeps the constructor, ``forward`` / ``infer_image`` signatures, attribute
 names and state-dict keys of upstream, so ``run.py:120-149`` and ``lightning_model.py:116-140``
 work unchanged, but the arithmetic runs in libdav2_b200.so (tcgen05 GEMMs / implicit-GEMM convs,
-fused attention, ...).  The ``nn`` layers below are PARAMETER CONTAINERS ONLY (they give the
+fused attention, ...).  One extra keyword, ``precision`` ("fp16" default = the reference's Lightning
+``16-mixed`` AMP, configs/trainer/default.yaml:4; or "bf16"), picks the tensor-core operand format;
+accumulation, the residual stream, LayerNorm statistics and softmax are always fp32.  The ``nn`` layers below are PARAMETER CONTAINERS ONLY (they give the
 upstream parameter names and shapes); they are never called.  No CPU path exists: calling
 ``forward`` with the module or input off the GPU raises.
 """
@@ -94,8 +96,11 @@ def _head_params(D: int, Fe: int, oc) -> nn.Module:
 
 class DepthAnythingV2(nn.Module):
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False,
-                 use_clstoken=False, max_depth=20.0):
+                 use_clstoken=False, max_depth=20.0, precision="fp16"):
         super().__init__()
+        if precision not in ("fp16", "bf16"):
+            raise ValueError("precision must be 'fp16' (the reference's AMP 16-mixed; default) or 'bf16'")
+        self.precision = precision
         if encoder not in _ENCODERS:
             raise ValueError(f"unsupported encoder {encoder!r} (vits | vitb | vitl)")
         if use_bn or use_clstoken:
@@ -142,7 +147,8 @@ class DepthAnythingV2(nn.Module):
         lib = _lib.load()
         self._release()
         D, depth, heads, Fe, oc = self._cfg
-        cfg = Dav2Config(D, depth, heads, Fe, (C.c_int32 * 4)(*oc), (C.c_int32 * 4)(*_TAPS[self.encoder]), float(self.max_depth))
+        cfg = Dav2Config(D, depth, heads, Fe, (C.c_int32 * 4)(*oc), (C.c_int32 * 4)(*_TAPS[self.encoder]), float(self.max_depth),
+                         _lib.FMT_BF16 if self.precision == "bf16" else _lib.FMT_F16)
         h = C.c_void_p()
         with torch.cuda.device(device):
             check(lib.dav2_create(C.byref(h), C.byref(cfg)), "dav2_create")

@@ -16,80 +16,97 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0) -> torch.Tensor:
-    """act(a[M,K] @ w[N,K]^T + bias) -> bf16 [M,N]   (act: 0 none, 1 GELU(erf), 2 ReLU)."""
+def _fmt(*tensors) -> int:
+    """fp16 / bf16 operand format code from the tensors' (common) dtype."""
+    dt = tensors[0].dtype
+    if any(t is not None and t.dtype != dt for t in tensors):
+        raise _lib.Dav2Error("all 16-bit operands of one call must share a dtype")
+    if dt == torch.float16:
+        return _lib.FMT_F16
+    if dt == torch.bfloat16:
+        return _lib.FMT_BF16
+    raise _lib.Dav2Error(f"16-bit operand must be torch.float16 or torch.bfloat16, got {dt}")
+
+
+def linear_h16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0) -> torch.Tensor:
+    """act(a[M,K] @ w[N,K]^T + bias) -> [M,N] in the operands' 16-bit dtype   (act: 0 none, 1 GELU(erf), 2 ReLU)."""
     require_cuda(a, "a"); require_cuda(w, "w")
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.shape[1] == w.shape[1]
+    fmt = _fmt(a, w)
+    assert a.shape[1] == w.shape[1]
     M, K = a.shape
     N = w.shape[0]
-    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    out = torch.empty(M, N, dtype=a.dtype, device=a.device)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
-    check(_lib.load().dav2_linear_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, act,
-                                       current_stream_ptr(a.device)), "dav2_linear_bf16")
+    check(_lib.load().dav2_linear_h16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, act, fmt,
+                                      current_stream_ptr(a.device)), "dav2_linear_h16")
     return out
 
 
 def linear_resid_(x: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
     """x[M,N] (fp32, in place) += gamma * (a @ w^T + bias)."""
     require_cuda(x, "x"); require_cuda(a, "a"); require_cuda(w, "w")
-    assert x.dtype == torch.float32 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    fmt = _fmt(a, w)
+    assert x.dtype == torch.float32
     M, K = a.shape
     N = w.shape[0]
     assert x.shape == (M, N)
-    check(_lib.load().dav2_linear_resid(a.data_ptr(), w.data_ptr(), _ptr(bias), gamma.data_ptr(), x.data_ptr(), M, N, K,
+    check(_lib.load().dav2_linear_resid(a.data_ptr(), w.data_ptr(), _ptr(bias), gamma.data_ptr(), x.data_ptr(), M, N, K, fmt,
                                         current_stream_ptr(a.device)), "dav2_linear_resid")
     return x
 
 
-def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
-    """Conv2d weight [Cout,Cin,3,3] (any float dtype) -> bf16 [Cout, 9*Cpad], tap-major, Cpad=ceil64(Cin)."""
+def pack_conv3x3_weight(w: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Conv2d weight [Cout,Cin,3,3] -> 16-bit [Cout, 9*Cpad], tap-major, Cpad=ceil64(Cin)."""
+    dtype = dtype or w.dtype
     Cout, Cin = w.shape[:2]
     Cpad = (Cin + 63) // 64 * 64
-    p = torch.zeros(Cout, 9, Cpad, dtype=torch.bfloat16, device=w.device)
-    p[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    p = torch.zeros(Cout, 9, Cpad, dtype=dtype, device=w.device)
+    p[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(dtype)
     return p.reshape(Cout, 9 * Cpad).contiguous()
 
 
-def conv3x3_bf16(x, wp, bias=None, add1=None, add2=None, act: int = 0, want_relu: bool = False):
-    """3x3/pad1 conv on NHWC bf16: x [B,H,W,Cin], wp from pack_conv3x3_weight -> out [B,H,W,Cout] (, relu(out))."""
+def conv3x3_h16(x, wp, bias=None, add1=None, add2=None, act: int = 0, want_relu: bool = False):
+    """3x3/pad1 conv on NHWC fp16/bf16: x [B,H,W,Cin], wp from pack_conv3x3_weight -> out [B,H,W,Cout] (, relu(out))."""
     require_cuda(x, "x"); require_cuda(wp, "wp")
+    fmt = _fmt(x, wp, add1, add2)
     B, H, W, Cin = x.shape
     Cout = wp.shape[0]
-    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(B, H, W, Cout, dtype=x.dtype, device=x.device)
     out_relu = torch.empty_like(out) if want_relu else None
-    check(_lib.load().dav2_conv3x3_bf16(x.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(add1), _ptr(add2), out.data_ptr(),
-                                        _ptr(out_relu), B, H, W, Cin, Cout, act, current_stream_ptr(x.device)),
-          "dav2_conv3x3_bf16")
+    check(_lib.load().dav2_conv3x3_h16(x.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(add1), _ptr(add2), out.data_ptr(),
+                                       _ptr(out_relu), B, H, W, Cin, Cout, act, fmt, current_stream_ptr(x.device)),
+          "dav2_conv3x3_h16")
     return (out, out_relu) if want_relu else out
 
 
-def attention_bf16(qkv: torch.Tensor, B: int, N: int, D: int) -> torch.Tensor:
-    """qkv bf16 [B*N, 3D] (q pre-scaled) -> softmax(q k^T) v, bf16 [B*N, D]; heads of 64."""
+def attention_h16(qkv: torch.Tensor, B: int, N: int, D: int) -> torch.Tensor:
+    """qkv fp16/bf16 [B*N, 3D] (q pre-scaled) -> softmax(q k^T) v, same dtype [B*N, D]; heads of 64."""
     require_cuda(qkv, "qkv")
-    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * N, 3 * D)
-    out = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
-    check(_lib.load().dav2_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, N, D, current_stream_ptr(qkv.device)),
-          "dav2_attention_bf16")
+    fmt = _fmt(qkv)
+    assert qkv.shape == (B * N, 3 * D)
+    out = torch.empty(B * N, D, dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().dav2_attention_h16(qkv.data_ptr(), out.data_ptr(), B, N, D, fmt, current_stream_ptr(qkv.device)),
+          "dav2_attention_h16")
     return out
 
 
-def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, out_dtype=torch.float16) -> torch.Tensor:
     require_cuda(x, "x")
     assert x.dtype == torch.float32
     rows, D = x.shape
-    out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().dav2_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, D, eps,
+    out = torch.empty(rows, D, dtype=out_dtype, device=x.device)
+    check(_lib.load().dav2_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, D, eps, _fmt(out),
                                      current_stream_ptr(x.device)), "dav2_layernorm")
     return out
 
 
-def bilinear_nhwc_bf16(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+def bilinear_nhwc_h16(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
     require_cuda(x, "x")
     B, Hi, Wi, Cc = x.shape
-    out = torch.empty(B, Ho, Wo, Cc, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().dav2_bilinear_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, Cc,
-                                              current_stream_ptr(x.device)), "dav2_bilinear_nhwc_bf16")
+    out = torch.empty(B, Ho, Wo, Cc, dtype=x.dtype, device=x.device)
+    check(_lib.load().dav2_bilinear_nhwc_h16(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, Cc, _fmt(x),
+                                             current_stream_ptr(x.device)), "dav2_bilinear_nhwc_h16")
     return out
 
 

@@ -39,6 +39,8 @@ typedef struct dav2_config {
   int32_t out_channels[4];/* reassemble widths, run.py:97-118                  */
   int32_t tap_layers[4];  /* 0-based block indices tapped for the DPT head     */
   float max_depth;        /* sigmoid scale, run.py:76 / configs/model/large.yaml:3 */
+  int32_t precision;      /* tensor-core operand format: 0 = fp16 (the reference's AMP '16-mixed',
+                             configs/trainer/default.yaml:4), 1 = bf16; accumulation is always fp32 */
 } dav2_config;
 
 int dav2_create(dav2_model** out, const dav2_config* cfg);
@@ -46,7 +48,7 @@ void dav2_destroy(dav2_model* m);
 
 /* load_state_dict (run.py:128-147, lightning_model.py:130-140): one call per upstream state-dict
  * key ("pretrained.blocks.3.attn.qkv.weight", ...).  `data` is HOST fp32, C-contiguous, `shape`
- * its dims.  The library converts / re-lays-out into its kernel formats (bf16 K-major GEMM operands,
+ * its dims.  The library converts / re-lays-out into its kernel formats (fp16/bf16 K-major GEMM operands,
  * tap-major 3x3 filters, pixel-shuffle-major transposed-conv filters, q pre-scaled by 1/8).
  * Unknown keys return a negative code (the Python layer implements strict=False on top). */
 int dav2_set_weight(dav2_model* m, const char* key, const float* data, const int64_t* shape, int32_t ndim);
@@ -62,7 +64,7 @@ int dav2_set_pos_embed(dav2_model* m, int32_t ph, int32_t pw, const float* table
 int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W, float* depth, void* stream);
 
 /* Parity / debugging: look up an internal activation buffer of the LAST forward by name
- * ("tap0".."tap3" bf16 [B*ph*pw, D]; "x" fp32 residual stream; "path1" ...).  Returns device ptr + bytes. */
+ * ("tap0".."tap3" h16 [B*ph*pw, D]; "x" fp32 residual stream; "path1" ...).  Returns device ptr + bytes. */
 int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* bytes);
 /* Copy the first `bytes` of that buffer into caller-owned device memory `dst` (async on `stream`). */
 int dav2_debug_read(dav2_model* m, const char* name, void* dst, int64_t bytes, void* stream);
@@ -103,26 +105,27 @@ int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW
  * [N+1,12] = rows of [R|t] with R = Rotation.from_quat(q).as_matrix() (depth_to_pointcloud.py:168-173). */
 int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* abs7, double* T12, void* stream);
 
-/* Operator-level entry points (unit parity tests + reuse): bf16 device operands.
- *   C[M,N] = act(A[M,K] * W[N,K]^T + bias)    A, W, C bf16 row-major; bias fp32 or NULL; act 0/1(GELU)/2(ReLU) */
-int dav2_linear_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
-                     int32_t act, void* stream);
+/* Operator-level entry points (unit parity tests + reuse).  "h16" operands are 16-bit device tensors whose
+ * numeric format is given by `fmt` (0 = fp16, 1 = bf16); accumulation is fp32.
+ *   C[M,N] = act(A[M,K] * W[N,K]^T + bias)    A, W, C h16 row-major; bias fp32 or NULL; act 0/1(GELU)/2(ReLU) */
+int dav2_linear_h16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                    int32_t act, int32_t fmt, void* stream);
 /*   x[M,N](fp32) += gamma[N] * (A[M,K] * W[N,K]^T + bias[N])   (LayerScale + residual epilogue) */
 int dav2_linear_resid(const void* A, const void* W, const float* bias, const float* gamma, float* x, int32_t M,
-                      int32_t N, int32_t K, void* stream);
-/*   3x3 / pad 1 / stride 1 conv, NHWC bf16: in [B,H,W,Cin], Wp [Cout, 9*Cpad] (tap-major, Cpad = ceil64(Cin)),
+                      int32_t N, int32_t K, int32_t fmt, void* stream);
+/*   3x3 / pad 1 / stride 1 conv, NHWC h16: in [B,H,W,Cin], Wp [Cout, 9*Cpad] (tap-major, Cpad = ceil64(Cin)),
  *   out [B,H,W,Cout] = act(conv + bias) + add1 + add2; out_relu (optional) = relu(out). */
-int dav2_conv3x3_bf16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
-                      void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                      int32_t act, void* stream);
-/*   softmax(q k^T) v per (image, head), d_head 64, q pre-scaled: qkv bf16 [B*N, 3*D] -> out bf16 [B*N, D] */
-int dav2_attention_bf16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, void* stream);
-/*   LayerNorm(eps) fp32 [rows, D] -> bf16 */
+int dav2_conv3x3_h16(const void* in, const void* Wp, const float* bias, const void* add1, const void* add2,
+                     void* out, void* out_relu, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                     int32_t act, int32_t fmt, void* stream);
+/*   softmax(q k^T) v per (image, head), d_head 64, q pre-scaled: qkv h16 [B*N, 3*D] -> out h16 [B*N, D] */
+int dav2_attention_h16(const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t fmt, void* stream);
+/*   LayerNorm(eps) fp32 [rows, D] -> h16 */
 int dav2_layernorm(const float* x, const float* w, const float* b, void* out, int64_t rows, int32_t D, float eps,
-                   void* stream);
-/*   bilinear align_corners=True, NHWC bf16 */
-int dav2_bilinear_nhwc_bf16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
-                            int32_t C, void* stream);
+                   int32_t fmt, void* stream);
+/*   bilinear align_corners=True, NHWC h16 */
+int dav2_bilinear_nhwc_h16(const void* in, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                           int32_t C, int32_t fmt, void* stream);
 
 /* Per-kernel-class timing with CUDA events recorded on the launching stream (bench.py's live roofline
  * measurement).  dav2_profile_report synchronises on the pending events, then writes a JSON object

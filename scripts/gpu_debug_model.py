@@ -11,8 +11,10 @@ enc = sys.argv[1] if len(sys.argv) > 1 else "vits"
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 70
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 98
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+prec = sys.argv[5] if len(sys.argv) > 5 else "fp16"
+HD = torch.bfloat16 if prec == "bf16" else torch.float16
 oracle = O.build_oracle(enc, seed=0)
-m = DepthAnythingV2(**MODEL_CONFIGS[enc]).cuda().eval()
+m = DepthAnythingV2(**MODEL_CONFIGS[enc], precision=prec).cuda().eval()
 m.load_state_dict(oracle.state_dict())
 x = O.synthetic_frames(B, H, W, seed=11)
 ph, pw = H // 14, W // 14
@@ -47,17 +49,17 @@ def rep(name, g, r):
 
 hh = [4 * ph, 2 * ph, ph, (ph + 1) // 2]; ww = [4 * pw, 2 * pw, pw, (pw + 1) // 2]
 for i, (t, _c) in enumerate(taps):
-    rep(f"tap{i}", m.debug_buffer(f"tap{i}", torch.bfloat16, (B, P, D)), t)
+    rep(f"tap{i}", m.debug_buffer(f"tap{i}", HD, (B, P, D)), t)
 for i in range(4):
-    rep(f"proj{i}", m.debug_buffer(f"proj{i}", torch.bfloat16, (B, ph, pw, oc[i])), cap[f"proj{i}"].permute(0, 2, 3, 1))
+    rep(f"proj{i}", m.debug_buffer(f"proj{i}", HD, (B, ph, pw, oc[i])), cap[f"proj{i}"].permute(0, 2, 3, 1))
     if i != 2:
         nm = f"lvl{i}"
-        rep(nm, m.debug_buffer(nm, torch.bfloat16, (B, hh[i], ww[i], oc[i])), cap[f"lvl{i}"].permute(0, 2, 3, 1))
-    rep(f"rn{i}", m.debug_buffer(f"rn{i}", torch.bfloat16, (B, hh[i], ww[i], Fe)), cap[f"rn{i}"].permute(0, 2, 3, 1))
+        rep(nm, m.debug_buffer(nm, HD, (B, hh[i], ww[i], oc[i])), cap[f"lvl{i}"].permute(0, 2, 3, 1))
+    rep(f"rn{i}", m.debug_buffer(f"rn{i}", HD, (B, hh[i], ww[i], Fe)), cap[f"rn{i}"].permute(0, 2, 3, 1))
 for i in (4, 3, 2, 1):
     r = cap[f"path{i}"].permute(0, 2, 3, 1)
-    rep(f"path{i}", m.debug_buffer(f"path{i}", torch.bfloat16, tuple(r.shape)), r)
+    rep(f"path{i}", m.debug_buffer(f"path{i}", HD, tuple(r.shape)), r)
 r = cap["out1"].permute(0, 2, 3, 1)
-rep("out1", m.debug_buffer("out1", torch.bfloat16, tuple(r.shape)), r)
+rep("out1", m.debug_buffer("out1", HD, tuple(r.shape)), r)
 rep("depth", got, ref)
 print("ref depth mean/std", float(ref.mean()), float(ref.std()))

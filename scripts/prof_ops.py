@@ -1,0 +1,42 @@
+"""Operator-shaped launches of the hot kernels at the vitl B=64 sizes, for ncu (GPU box only).
+Usage: python scripts/prof_ops.py [gemm|conv|attn|all] [reps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dav2_b200 import ops
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dt = torch.float16
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(0)
+def rnd(*shape, scale=1.0, dtype=dt):
+    return (torch.randn(*shape, generator=g, device=dev) * scale).to(dtype)
+
+M, D = 64 * 1370, 1024
+if what in ("gemm", "all"):
+    a = rnd(M, D); w_qkv = rnd(3 * D, D, scale=D ** -0.5); b_qkv = rnd(3 * D, dtype=torch.float32)
+    w_fc1 = rnd(4 * D, D, scale=D ** -0.5); b_fc1 = rnd(4 * D, dtype=torch.float32)
+    hid = rnd(M, 4 * D); w_fc2 = rnd(D, 4 * D, scale=(4 * D) ** -0.5); b_d = rnd(D, dtype=torch.float32)
+    w_proj = rnd(D, D, scale=D ** -0.5); gamma = rnd(D, dtype=torch.float32)
+    x = rnd(M, D, dtype=torch.float32)
+    for _ in range(reps):
+        ops.linear_h16(a, w_qkv, b_qkv, 0)          # qkv   87680 x 3072 x 1024
+        ops.linear_h16(a, w_fc1, b_fc1, 1)          # fc1   87680 x 4096 x 1024 + GELU
+        ops.linear_resid_(x, hid, w_fc2, b_d, gamma)  # fc2   87680 x 1024 x 4096 + residual
+        ops.linear_resid_(x, a, w_proj, b_d, gamma)   # proj  87680 x 1024 x 1024 + residual
+if what in ("conv", "all"):
+    B = 64
+    x1 = rnd(B, 148, 148, 256); w1 = ops.pack_conv3x3_weight(rnd(256, 256, 3, 3, scale=(9 * 256) ** -0.5))
+    bias = rnd(256, dtype=torch.float32)
+    x2 = rnd(B, 296, 296, 256); w2 = ops.pack_conv3x3_weight(rnd(128, 256, 3, 3, scale=(9 * 256) ** -0.5))
+    bias2 = rnd(128, dtype=torch.float32)
+    for _ in range(reps):
+        ops.conv3x3_h16(x1, w1, bias, None, None, 2)    # RCU conv at 148^2, F=256
+        ops.conv3x3_h16(x2, w2, bias2, None, None, 0)   # output_conv1 at 296^2, 256 -> 128
+if what in ("attn", "all"):
+    qkv = rnd(M, 3 * D)
+    for _ in range(reps):
+        ops.attention_h16(qkv, 64, 1370, D)
+torch.cuda.synchronize()
+print("ok")
