@@ -11,7 +11,7 @@
 //                                     running O kept in registers (o = o*alpha + O_part)
 // Q was pre-scaled by d^-1/2 = 0.125 (folded exactly into the qkv weights), so S needs no scale.
 // Reads qkv h16 [B*N, 3*D] (q | k | v, head h at columns h*64), writes out h16 [B*N, D].
-#include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace dav2 {
 
@@ -34,6 +34,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return r;
+}
+
+template <bool FP16>
 __global__ void __launch_bounds__(192, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -145,7 +152,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         tmem_ld_wait();
         if (nvalid >= (c + 1) * 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -174,14 +181,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         tmem_ld32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (nvalid >= (c + 1) * 32) {  // warp-uniform: every key of this chunk is inside the image
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
-          float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
-          if (c * 32 + 2 * i >= nvalid) e0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= nvalid) e1 = 0.f;
-          rowsum += e0 + e1;
-          pk[i] = pack_h2(e0, e1, p.fmt);
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
+            rowsum += e0 + e1;
+            pk[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
+            float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
+            if (c * 32 + 2 * i >= nvalid) e0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= nvalid) e1 = 0.f;
+            rowsum += e0 + e1;
+            pk[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
+          }
         }
         const uint32_t rowbase = sP + (uint32_t)(c >> 1) * ATT_TILE + (uint32_t)r * 128u;
 #pragma unroll
@@ -216,10 +233,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 u;
-        u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv, p.fmt);
-        u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv, p.fmt);
-        u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv, p.fmt);
-        u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv, p.fmt);
+        u.x = (FP16 ? pack2<FMT_F16>(o[8 * g] * inv, o[8 * g + 1] * inv) : pack2<FMT_BF16>(o[8 * g] * inv, o[8 * g + 1] * inv));
+        u.y = (FP16 ? pack2<FMT_F16>(o[8 * g + 2] * inv, o[8 * g + 3] * inv) : pack2<FMT_BF16>(o[8 * g + 2] * inv, o[8 * g + 3] * inv));
+        u.z = (FP16 ? pack2<FMT_F16>(o[8 * g + 4] * inv, o[8 * g + 5] * inv) : pack2<FMT_BF16>(o[8 * g + 4] * inv, o[8 * g + 5] * inv));
+        u.w = (FP16 ? pack2<FMT_F16>(o[8 * g + 6] * inv, o[8 * g + 7] * inv) : pack2<FMT_BF16>(o[8 * g + 6] * inv, o[8 * g + 7] * inv));
         *reinterpret_cast<uint4*>(dst + 8 * g) = u;
       }
     }
@@ -241,7 +258,8 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;
   static bool configured = false;
   if (!configured) {
-    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured = true;
   }
   AttnParams p;
@@ -254,7 +272,8 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   p.fmt = fmt;
   dim3 grid((N + 127) / 128, D / 64, B);
   ProfScope ps(PC_ATTN, 4.0 * B * (D / 64) * (double)N * N * 64.0, 2.0 * 4.0 * B * (double)N * D, stream);
-  attention_kernel<<<grid, 192, ATT_SMEM, stream>>>(tm, p);
+  if (fmt == FMT_F16) attention_kernel<true><<<grid, 192, ATT_SMEM, stream>>>(tm, p);
+  else attention_kernel<false><<<grid, 192, ATT_SMEM, stream>>>(tm, p);
   DAV2_LAUNCH_OK();
   return 0;
 }

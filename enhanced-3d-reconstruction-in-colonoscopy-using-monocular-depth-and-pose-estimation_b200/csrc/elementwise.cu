@@ -2,6 +2,7 @@
 // cls-token row, strided-conv im2col, bilinear (align_corners=True) NHWC resampler, depth resampler.
 // All are coalesced + 16-byte vectorised; grids are sized in multiples of the SM count.
 #include "elementwise.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace dav2 {
 
@@ -178,55 +179,50 @@ int launch_im2col_s2(const h16* in, h16* A, int B, int H, int W, int C, cudaStre
 // Bilinear resize, align_corners=True, NHWC h16 -> NHWC h16 (fp32 blend), 8 channels per thread.
 // src coordinate = dst * (in-1)/(out-1), exactly like F.interpolate(..., align_corners=True).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restrict__ in, h16* __restrict__ out, int B,
-                                                            int Hi, int Wi, int Ho, int Wo, int C, float sy, float sx, int fmt) {
-  const int c8 = C / 8;
-  const long long total = (long long)B * Ho * Wo * c8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % c8);
-    long long t = i / c8;
-    const int xo = (int)(t % Wo);
-    t /= Wo;
-    const int yo = (int)(t % Ho);
-    const int b = (int)(t / Ho);
-    const float fy = sy * yo, fx = sx * xo;
-    int y0 = (int)fy, x0 = (int)fx;
-    y0 = min(y0, Hi - 1);
-    x0 = min(x0, Wi - 1);
-    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
-    const float wy = fy - (float)y0, wx = fx - (float)x0;
-    const h16* base = in + (long long)b * Hi * Wi * C;
-    const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
-    const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
-    const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
-    const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
-    const uint32_t* a = &p00.x;
-    const uint32_t* bq = &p01.x;
-    const uint32_t* c = &p10.x;
-    const uint32_t* d = &p11.x;
-    uint4 o;
-    uint32_t* ow = &o.x;
-    const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+template <int FMT>
+__global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restrict__ in, h16* __restrict__ out, int Hi, int Wi,
+                                                            int Ho, int Wo, int C, float sy, float sx) {
+  // grid = (ceil(Wo*C/8 / 256), Ho, B): the row-level interpolation terms are block-uniform, and the only
+  // per-thread division is a 32-bit one (64-bit div/mod chains made the first version latency bound).
+  const int c8 = C >> 3;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wo * c8) return;
+  const int xo = t / c8, cv = t - xo * c8;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const float fy = sy * yo, fx = sx * xo;
+  const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
+  const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+  const float wy = fy - (float)y0, wx = fx - (float)x0;
+  const h16* base = in + (long long)b * Hi * Wi * C;
+  const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
+  const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
+  const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
+  const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
+  const uint32_t* a = &p00.x;
+  const uint32_t* bq = &p01.x;
+  const uint32_t* c = &p10.x;
+  const uint32_t* d = &p11.x;
+  uint4 o;
+  uint32_t* ow = &o.x;
+  const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fa = unpack_h2(a[k], fmt), fb = unpack_h2(bq[k], fmt), fc = unpack_h2(c[k], fmt), fd = unpack_h2(d[k], fmt);
-      ow[k] = pack_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                      w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, fmt);
-    }
-    reinterpret_cast<uint4*>(out)[i] = o;
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = unpack2<FMT>(a[k]), fb = unpack2<FMT>(bq[k]), fc = unpack2<FMT>(c[k]), fd = unpack2<FMT>(d[k]);
+    ow[k] = pack2<FMT>(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
   }
+  __stcs(reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Wo + xo) * C) + cv, o);
 }
 
 int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int fmt, cudaStream_t stream) {
   DAV2_CHECK(C % 8 == 0, "bilinear: C=%d must be a multiple of 8", C);
+  DAV2_CHECK(Ho <= 65535 && B <= 65535, "bilinear: Ho / B exceed the grid limits");
   const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)B * Ho * Wo * (C / 8);
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)sm_count() * 32;
-  if (blocks > cap) blocks = cap;
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  dim3 grid((unsigned)((Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)B);
   ProfScope ps(PC_RESAMPLE, 0.0, 2.0 * C * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
-  bilinear_nhwc_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, B, Hi, Wi, Ho, Wo, C, sy, sx, fmt);
+  if (fmt == FMT_BF16) bilinear_nhwc_kernel<FMT_BF16><<<grid, 256, 0, stream>>>(in, out, Hi, Wi, Ho, Wo, C, sy, sx);
+  else bilinear_nhwc_kernel<FMT_F16><<<grid, 256, 0, stream>>>(in, out, Hi, Wi, Ho, Wo, C, sy, sx);
   DAV2_LAUNCH_OK();
   return 0;
 }

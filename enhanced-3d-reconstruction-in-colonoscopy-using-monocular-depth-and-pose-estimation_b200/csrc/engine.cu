@@ -311,14 +311,16 @@ int gemm_linear(int mode, const h16* A, int M, int K, long long lda, const h16* 
                 cudaStream_t stream) {
   DAV2_CHECK(N % 4 == 0, "gemm: N=%d must be a multiple of 4", N);
   const int bn = pick_bn(N);
-  CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128)) return rc;
-  if (int rc = make_tmap_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn)) return rc;
   p.M = M; p.N = N; p.K = K;
   p.num_kb = (K + 63) / 64;
   p.tiles_m = (M + 127) / 128;
   p.tiles_n = (N + bn - 1) / bn;
+  const bool two_cta = gemm2_eligible(bn, mode, p.tiles_m);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128)) return rc;
+  if (int rc = make_tmap_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(two_cta ? bn / 2 : bn))) return rc;
   ProfScope ps(PC_GEMM, 2.0 * M * (double)N * K, 2.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
+  if (two_cta) return launch_gemm2(bn, mode, tmA, tmB, p, stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }
 
@@ -344,9 +346,11 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   pick_conv_tile(H, W, &tw, &th);
   const int cblocks = (Cin + 63) / 64;
   const int Kp = 9 * cblocks * 64;
+  const int tiles_m_all = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+  const bool two_cta = gemm2_eligible(bn, mode, tiles_m_all);
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, (uint32_t)tw, (uint32_t)th)) return rc;
-  if (int rc = make_tmap_2d(&tmB, Wp, (uint64_t)Cout, (uint64_t)Kp, (uint64_t)Kp, (uint32_t)bn)) return rc;
+  if (int rc = make_tmap_2d(&tmB, Wp, (uint64_t)Cout, (uint64_t)Kp, (uint64_t)Kp, (uint32_t)(two_cta ? bn / 2 : bn))) return rc;
   p.M = B * H * W; p.N = Cout; p.K = Kp;
   p.num_kb = 9 * cblocks;
   p.cblocks = cblocks;
@@ -356,7 +360,8 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   p.tiles_m = B * p.tiles_x * p.tiles_y;
   p.tiles_n = (Cout + bn - 1) / bn;
   if (p.ldo == 0) p.ldo = Cout;
-  ProfScope ps(PC_CONV, 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 2.0 * ((double)B * H * W * (Cin + Cout) + 9.0 * Cin * Cout), stream);
+  ProfScope ps2(PC_CONV, 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 2.0 * ((double)B * H * W * (Cin + Cout) + 9.0 * Cin * Cout), stream);
+  if (two_cta) return launch_gemm2(bn, mode, tmA, tmB, p, stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }
 

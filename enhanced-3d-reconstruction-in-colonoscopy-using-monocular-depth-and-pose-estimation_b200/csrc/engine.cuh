@@ -9,7 +9,7 @@
 
 #include "../../include/dav2_b200.h"
 #include "elementwise.cuh"
-#include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 
 namespace dav2 {
 

@@ -1,5 +1,7 @@
 // Host launcher + template instantiations for the tcgen05 GEMM / implicit-GEMM conv kernel.
-#include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
+
+#include <stdlib.h>
 
 namespace dav2 {
 
@@ -59,6 +61,55 @@ int launch_gemm(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB
   }
   set_last_error("launch_gemm: unsupported (bn=%d, mode=%d)", bn, mode);
   return -3;
+}
+
+template <int BN, int MODE>
+static int launch2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    DAV2_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  if (pairs <= 0) return 0;
+  const int max_pairs = sm_count() / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  gemm2_tcgen05_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+#define DISPATCH2_BN(MODE)                                               \
+  switch (bn) {                                                          \
+    case 256: return launch2_t<256, MODE>(tmA, tmB, p, stream);          \
+    case 128: return launch2_t<128, MODE>(tmA, tmB, p, stream);          \
+    default: break;                                                      \
+  }
+
+// 2-CTA (cta_group::2) kernel: bn in {128, 256}; tmB must have been encoded with box rows bn/2.
+int launch_gemm2(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                 cudaStream_t stream) {
+  switch (mode) {
+    case GM_LINEAR_BF16: DISPATCH2_BN(GM_LINEAR_BF16); break;
+    case GM_LINEAR_RESID: DISPATCH2_BN(GM_LINEAR_RESID); break;
+    case GM_PATCH: DISPATCH2_BN(GM_PATCH); break;
+    case GM_CONVT: DISPATCH2_BN(GM_CONVT); break;
+    case GM_CONV_BF16: DISPATCH2_BN(GM_CONV_BF16); break;
+    default: break;
+  }
+  set_last_error("launch_gemm2: unsupported (bn=%d, mode=%d)", bn, mode);
+  return -3;
+}
+
+bool gemm2_eligible(int bn, int mode, int tiles_m) {
+  static int force = -1;  // DAV2_GEMM2=0 disables, =1 (default) enables the 2-CTA kernel
+  if (force < 0) {
+    const char* e = getenv("DAV2_GEMM2");
+    force = (e && e[0] == '0') ? 0 : 1;
+  }
+  return force == 1 && mode != GM_CONV_HEAD && (bn == 128 || bn == 256) && tiles_m >= 2;
 }
 
 }  // namespace dav2

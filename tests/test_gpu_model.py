@@ -73,7 +73,9 @@ def test_batch_consistency_and_strict_false():
     whole = m(x)
     for b in range(3):
         single = m(x[b:b + 1].contiguous())
-        assert torch.equal(single[0], whole[b])
+        # different batch sizes take different kernels (1-CTA RMW vs 2-CTA bulk-reduce epilogue, fma vs mul+add):
+        # agreement is at the 16-bit rounding-noise level, not bitwise
+        assert float((single[0] - whole[b]).abs().max() / whole[b].abs().max()) < DEPTH_TOL
     # lightning_model.py:130-140: encoder-only partial load with strict=False must work
     from dav2_b200.dpt import MODEL_CONFIGS, DepthAnythingV2
     m2 = DepthAnythingV2(**MODEL_CONFIGS["vits"])
