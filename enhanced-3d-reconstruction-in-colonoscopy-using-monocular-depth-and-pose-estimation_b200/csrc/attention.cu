@@ -4,7 +4,7 @@
 // softmax (MUFU-bound) overlaps the other's tensor-core work.
 //   warp 0 (1 lane) : TMA producer  - Q once, then K/V tiles through a 2-deep smem ring
 //   warp 1 (1 lane) : MMA issuer    - S = Q K^T (tcgen05, 128x128x64 -> TMEM cols [0,128)),
-//                                     O_part = P V (128x64x128 -> TMEM cols [128,192)), V is the
+//                                     O += P V (128x64x128 -> TMEM cols [128,192)), V is the
 //                                     MN-major B operand straight from the [token, 3D] qkv buffer
 //   warps 2..5      : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
 //                                     fp32, P -> h16 into 128B-swizzled smem (A operand of the PV MMA),
@@ -124,120 +124,116 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       for (int k = 0; k < 8; ++k) {
         const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
         const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
-        umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)(k != 0));
+        umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
       }
       umma_commit(BAR_O_FULL);
       umma_commit(BAR_KV_EMPTY + 8 * s);
     }
   } else if (warp >= 2) {
     // ---------------- softmax / output (one query row per thread) ----------------
+    // The whole S row (128 fp32) is pulled into registers with ONE exposed TMEM round trip, which frees the
+    // S buffer at once (the issuer overlaps S(j+1) with this tile's softmax).  O accumulates in TMEM across
+    // KV tiles; it is rescaled (TMEM load-scale-store) only when some row's running max grew by more than
+    // 2^8 since its reference max was taken ("lazy rescaling": P <= 256 is harmless in fp16/bf16 with fp32
+    // accumulation, and the final O / l is independent of the reference).
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, a_prev = 0.f;
-    uint32_t v[32];
+    float m_ref = -INFINITY, l = 0.f;
+    uint32_t sreg[128];
 
     for (int j = 0; j < p.nkv; ++j) {
       const int nvalid = p.N - j * 128;  // keys of this tile inside the image (>= 1)
       mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (nvalid >= (c + 1) * 32) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(BAR_S_EMPTY);  // S(j) is in registers: the issuer may overwrite the TMEM buffer with S(j+1)
+      if (nvalid < 128) {        // warp-uniform: tail tile, keys beyond the image never contribute
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i)
+          if (i >= nvalid) sreg[i] = 0xff800000u;  // -inf
+      }
+      float mx = __uint_as_float(sreg[0]);
+#pragma unroll
+      for (int i = 1; i < 127; i += 2) mx = fmax3(mx, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
+      mx = fmaxf(mx, __uint_as_float(sreg[127]));
+      bool o_waited = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const float m_new = fmaxf(m_ref, mx);
+        const bool need = (m_new - m_ref) * LOG2E > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) has finished accumulating into O
+          tc_fence_after();
+          o_waited = true;
+          const float alpha = need ? fast_exp2((m_ref - m_new) * LOG2E) : 1.0f;
+          if (need) m_ref = m_new;
+          l *= alpha;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[16];
+            tmem_ld16(tO + lane_addr + c * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st16(tO + lane_addr + c * 16, ov);
+          }
+          tmem_st_wait();
+          tc_fence_before();
         }
       }
-      const float m_new = mx;
-      const float a = fast_exp2((m - m_new) * LOG2E);  // m = -inf on the first tile -> 0
-      const float mscaled = m_new * LOG2E;
-      if (j > 0) {
-        // fold O_part(j-1) into the running output; it also frees the P buffer for P(j)
-        mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tO + lane_addr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], a_prev, __uint_as_float(v[i]));
-        }
-      }
-      // pass 2: P = exp2(S*log2e - m*log2e) -> h16 -> swizzled smem
+      const float mscaled = m_ref * LOG2E;
       float rowsum = 0.f;
-#pragma unroll 1
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i]), LOG2E, -mscaled));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 1]), LOG2E, -mscaled));
+        rowsum += e0 + e1;
+        sreg[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);  // in place: slot i <= 2i is already consumed
+      }
+      l += rowsum;
+      if (j > 0 && !o_waited) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P buffer
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        tmem_ld32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (nvalid >= (c + 1) * 32) {  // warp-uniform: every key of this chunk is inside the image
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
-            rowsum += e0 + e1;
-            pk[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -mscaled));
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -mscaled));
-            if (c * 32 + 2 * i >= nvalid) e0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= nvalid) e1 = 0.f;
-            rowsum += e0 + e1;
-            pk[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
-          }
-        }
         const uint32_t rowbase = sP + (uint32_t)(c >> 1) * ATT_TILE + (uint32_t)r * 128u;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t chunk = (uint32_t)((c & 1) * 4 + g) ^ ((uint32_t)r & 7u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(pk[4 * g]),
-                       "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(sreg[c * 16 + 4 * g]),
+                       "r"(sreg[c * 16 + 4 * g + 1]), "r"(sreg[c * 16 + 4 * g + 2]), "r"(sreg[c * 16 + 4 * g + 3])
                        : "memory");
         }
       }
-      tc_fence_before();
-      mbar_arrive(BAR_S_EMPTY);  // S(j) fully read: the issuer may overwrite it with S(j+1)
       fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor-core (async) proxy
       mbar_arrive(BAR_P_FULL);
-      l = fmaf(l, a, rowsum);
-      m = m_new;
-      a_prev = a;
     }
-    // last partial product
+    // final: O / l
     mbar_wait(BAR_O_FULL, (uint32_t)(p.nkv - 1) & 1u);
     tc_fence_after();
+    const float inv = 1.0f / l;
+    const bool row_ok = q0 + r < p.N;
+    h16* dst = p.out + (long long)(row0 + q0 + r) * p.D + h * 64;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      tmem_ld32(tO + lane_addr + c * 32, v);
+      uint32_t ov[32];
+      tmem_ld32(tO + lane_addr + c * 32, ov);
       tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], a_prev, __uint_as_float(v[i]));
-    }
-    if (q0 + r < p.N) {
-      const float inv = 1.0f / l;
-      h16* dst = p.out + (long long)(row0 + q0 + r) * p.D + h * 64;
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          uint32_t* uw = &u.x;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = (FP16 ? pack2<FMT_F16>(o[8 * g] * inv, o[8 * g + 1] * inv) : pack2<FMT_BF16>(o[8 * g] * inv, o[8 * g + 1] * inv));
-        u.y = (FP16 ? pack2<FMT_F16>(o[8 * g + 2] * inv, o[8 * g + 3] * inv) : pack2<FMT_BF16>(o[8 * g + 2] * inv, o[8 * g + 3] * inv));
-        u.z = (FP16 ? pack2<FMT_F16>(o[8 * g + 4] * inv, o[8 * g + 5] * inv) : pack2<FMT_BF16>(o[8 * g + 4] * inv, o[8 * g + 5] * inv));
-        u.w = (FP16 ? pack2<FMT_F16>(o[8 * g + 6] * inv, o[8 * g + 7] * inv) : pack2<FMT_BF16>(o[8 * g + 6] * inv, o[8 * g + 7] * inv));
-        *reinterpret_cast<uint4*>(dst + 8 * g) = u;
+          for (int k = 0; k < 4; ++k) {
+            const float f0 = __uint_as_float(ov[8 * g + 2 * k]) * inv, f1 = __uint_as_float(ov[8 * g + 2 * k + 1]) * inv;
+            uw[k] = FP16 ? pack2<FMT_F16>(f0, f1) : pack2<FMT_BF16>(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 32 + 8 * g) = u;
+        }
       }
     }
   }
