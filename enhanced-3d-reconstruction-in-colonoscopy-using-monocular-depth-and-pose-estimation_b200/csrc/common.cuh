@@ -236,17 +236,19 @@ inline uint16_t f2h_host(float x, int fmt) {
 // rounding of the product): one rcp + one ex2 instead of erff's ~30-instruction branchy path -- the fc1
 // epilogue applies it to 4096 columns per token and must keep pace with the MMA stream.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  // 15 instructions (2 MUFU): 0.5x(1+erf(z)) = hx + |hx|*erf(|z|) with hx = x/2, z = x/sqrt(2)
+  const float az = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-az * az * 1.4426950408889634f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
   const float erf_abs = fmaf(-poly, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, z));
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);
 }
 
 // ----------------------------------------------------------------------------------------------
