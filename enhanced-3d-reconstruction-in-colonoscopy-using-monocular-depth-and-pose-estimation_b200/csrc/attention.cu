@@ -81,53 +81,66 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
-  if (threadIdx.x == 0) {
-    // ---------------- TMA producer ----------------
-    mbar_expect_tx(BAR_Q, ATT_TILE);
-    tma_load_2d(sQ, &tmQKV, BAR_Q, h * 64, row0 + q0);
+  if (warp == 0) {
+    // ---------------- TMA producer (whole warp, elected lane issues) ----------------
+    if (elect_one()) {
+      mbar_expect_tx(BAR_Q, ATT_TILE);
+      tma_load_2d(sQ, &tmQKV, BAR_Q, h * 64, row0 + q0);
+    }
+    __syncwarp();
     for (int j = 0; j < p.nkv; ++j) {
       const int s = j & 1;
       mbar_wait(BAR_KV_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
-      mbar_expect_tx(BAR_KV_FULL + 8 * s, 2 * ATT_TILE);
-      tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
-      tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
+      if (elect_one()) {
+        mbar_expect_tx(BAR_KV_FULL + 8 * s, 2 * ATT_TILE);
+        tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
+        tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
+      }
+      __syncwarp();
     }
-  } else if (threadIdx.x == 32) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (whole warp, elected lane issues) ----------------
     const uint32_t idesc_s = make_idesc_h(128, 128, 0, 0, p.fmt);  // S = Q K^T : both K-major
     const uint32_t idesc_o = make_idesc_h(128, 64, 0, 1, p.fmt);   // O = P V   : V is MN-major
     const uint64_t qdesc = make_sw128_desc(sQ, 16, 1024);
     mbar_wait(BAR_Q, 0);
     mbar_wait(BAR_KV_FULL, 0);
     tc_fence_after();
-    {
+    if (elect_one()) {
       const uint64_t kdesc = make_sw128_desc(sK, 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
       umma_commit(BAR_S_FULL);
     }
+    __syncwarp();
     for (int j = 0; j < p.nkv; ++j) {
       const int s = j & 1;
       if (j + 1 < p.nkv) {
         const int s1 = (j + 1) & 1;
         mbar_wait(BAR_KV_FULL + 8 * s1, (uint32_t)((j + 1) >> 1) & 1u);
-        mbar_wait(BAR_S_EMPTY, (uint32_t)j & 1u);  // softmax finished reading S(j)
+        mbar_wait(BAR_S_EMPTY, (uint32_t)j & 1u);  // softmax has pulled S(j) into registers
         tc_fence_after();
-        const uint64_t kdesc = make_sw128_desc(sK + s1 * ATT_TILE, 16, 1024);
+        if (elect_one()) {
+          const uint64_t kdesc = make_sw128_desc(sK + s1 * ATT_TILE, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
-        umma_commit(BAR_S_FULL);
+          for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
+          umma_commit(BAR_S_FULL);
+        }
+        __syncwarp();
       }
-      mbar_wait(BAR_P_FULL, (uint32_t)j & 1u);  // P(j) in smem, O_part(j-1) consumed
+      mbar_wait(BAR_P_FULL, (uint32_t)j & 1u);  // P(j) in smem, any rescale of O finished
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
-        const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
-        umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
+          const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
+          umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
+        }
+        umma_commit(BAR_O_FULL);
+        umma_commit(BAR_KV_EMPTY + 8 * s);
       }
-      umma_commit(BAR_O_FULL);
-      umma_commit(BAR_KV_EMPTY + 8 * s);
+      __syncwarp();
     }
   } else if (warp >= 2) {
     // ---------------- softmax / output (one query row per thread) ----------------

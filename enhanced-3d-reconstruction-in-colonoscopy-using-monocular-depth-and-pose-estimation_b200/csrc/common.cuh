@@ -93,6 +93,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully active) warp; the same lane every time.  Role loops are executed by the WHOLE warp
+// (warp-uniform control flow keeps addresses / descriptors in uniform registers) and only the TMA / MMA /
+// commit instructions are predicated on the elected lane -- with a single-thread role branch ncu showed four
+// R2UR + ELECT per tcgen05.mma, i.e. the issue path, not the tensor pipe, bounded the N<=128 tiles.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -346,10 +346,14 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   pick_conv_tile(H, W, &tw, &th);
   const int cblocks = (Cin + 63) / 64;
   const int Kp = 9 * cblocks * 64;
+  // halo-reuse kernel: fixed 8 x 16 output tile, one (16 x 18)-pixel patch per channel block
+  const bool halo = conv_halo_eligible(bn, mode, B * ((W + 7) / 8) * ((H + 15) / 16));
+  if (halo) { tw = 8; th = 16; }
   const int tiles_m_all = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
-  const bool two_cta = gemm2_eligible(bn, mode, tiles_m_all);
+  const bool two_cta = halo || gemm2_eligible(bn, mode, tiles_m_all);
   CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, (uint32_t)tw, (uint32_t)th)) return rc;
+  if (int rc = make_tmap_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, (uint32_t)(halo ? 16 : tw),
+                              (uint32_t)(halo ? 18 : th))) return rc;
   if (int rc = make_tmap_2d(&tmB, Wp, (uint64_t)Cout, (uint64_t)Kp, (uint64_t)Kp, (uint32_t)(two_cta ? bn / 2 : bn))) return rc;
   p.M = B * H * W; p.N = Cout; p.K = Kp;
   p.num_kb = 9 * cblocks;
@@ -361,6 +365,7 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   p.tiles_n = (Cout + bn - 1) / bn;
   if (p.ldo == 0) p.ldo = Cout;
   ProfScope ps2(PC_CONV, 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 2.0 * ((double)B * H * W * (Cin + Cout) + 9.0 * Cin * Cout), stream);
+  if (halo) return launch_conv_halo(bn, tmA, tmB, p, stream);
   if (two_cta) return launch_gemm2(bn, mode, tmA, tmB, p, stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }

@@ -9,7 +9,7 @@
 
 #include "../../include/dav2_b200.h"
 #include "elementwise.cuh"
-#include "gemm2_tcgen05.cuh"
+#include "conv_halo_tcgen05.cuh"
 
 namespace dav2 {
 

@@ -148,8 +148,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_pt = pairs_m * p.tiles_n;
   const int pt0 = (int)(blockIdx.x >> 1), pt_stride = (int)(gridDim.x >> 1);
 
-  if (threadIdx.x == 0) {
-    // ================================ TMA producer (both CTAs) ==============================
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs; whole warp, elected lane issues) ======
     int stage = 0;
     uint32_t phase = 0;
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
@@ -169,24 +169,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t a_dst = base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
         const uint32_t full_leader = mapa_shared(FULL_BAR(stage), 0);
-        if (leader) mbar_expect_tx(FULL_BAR(stage), 2 * Cfg::STAGE_BYTES);
-        if (IS_CONV) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          tma_load_4d_2sm(a_dst, &tmA, full_leader, cb * 64, x0 + dx, y0 + dy, b);
-        } else {
-          tma_load_2d_2sm(a_dst, &tmA, full_leader, kb * 64, tm * 128);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(FULL_BAR(stage), 2 * Cfg::STAGE_BYTES);
+          if (IS_CONV) {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d_2sm(a_dst, &tmA, full_leader, cb * 64, x0 + dx, y0 + dy, b);
+          } else {
+            tma_load_2d_2sm(a_dst, &tmA, full_leader, kb * 64, tm * 128);
+          }
+          tma_load_2d_2sm(b_dst, &tmB, full_leader, kb * 64, tn * BN + (int)rank * (BN / 2));
         }
-        tma_load_2d_2sm(b_dst, &tmB, full_leader, kb * 64, tn * BN + (int)rank * (BN / 2));
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (threadIdx.x == 32 && leader) {
-    // ================================ MMA issuer (leader CTA only) ===========================
+  } else if (warp == 1 && leader) {
+    // ================================ MMA issuer (leader CTA; whole warp, elected lane issues) =======
     const uint32_t idesc = make_idesc_h(256, BN, 0, 0, p.fmt);
     int stage = 0;
     uint32_t phase = 0;
@@ -202,16 +205,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t a_addr = base + stage * Cfg::STAGE_BYTES;
         const uint64_t adesc = make_sw128_desc(a_addr, 16, 1024);
         const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_h16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-        umma_commit_2sm_mc(EMPTY_BAR(stage), 3);
+          for (int k = 0; k < 4; ++k)
+            umma_h16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm_mc(EMPTY_BAR(stage), 3);
+          if (kb == p.num_kb - 1) umma_commit_2sm_mc(TFULL_BAR(as), 3);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit_2sm_mc(TFULL_BAR(as), 3);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

@@ -79,8 +79,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
-  if (threadIdx.x == 0) {
-    // ================================ TMA producer =========================================
+  if (warp == 0) {
+    // ================================ TMA producer (whole warp, elected lane issues) ==========
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -98,24 +98,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(EMPTY_BAR(stage), phase ^ 1u);
         const uint32_t a_dst = base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-        mbar_expect_tx(FULL_BAR(stage), Cfg::STAGE_BYTES);
-        if (IS_CONV) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          tma_load_4d(a_dst, &tmA, FULL_BAR(stage), cb * 64, x0 + dx, y0 + dy, b);
-        } else {
-          tma_load_2d(a_dst, &tmA, FULL_BAR(stage), kb * 64, tm * 128);
+        if (elect_one()) {
+          mbar_expect_tx(FULL_BAR(stage), Cfg::STAGE_BYTES);
+          if (IS_CONV) {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(a_dst, &tmA, FULL_BAR(stage), cb * 64, x0 + dx, y0 + dy, b);
+          } else {
+            tma_load_2d(a_dst, &tmA, FULL_BAR(stage), kb * 64, tm * 128);
+          }
+          tma_load_2d(b_dst, &tmB, FULL_BAR(stage), kb * 64, tn * BN);
         }
-        tma_load_2d(b_dst, &tmB, FULL_BAR(stage), kb * 64, tn * BN);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ================================ MMA issuer ============================================
+  } else if (warp == 1) {
+    // ================================ MMA issuer (whole warp, elected lane issues) ============
     const uint32_t idesc = make_idesc_h(128, BN, 0, 0, p.fmt);
     int stage = 0;
     uint32_t phase = 0;
@@ -131,16 +134,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t a_addr = base + stage * Cfg::STAGE_BYTES;
         const uint64_t adesc = make_sw128_desc(a_addr, 16, 1024);
         const uint64_t bdesc = make_sw128_desc(a_addr + Cfg::A_BYTES, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_h16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-        umma_commit(EMPTY_BAR(stage));
+          for (int k = 0; k < 4; ++k)
+            umma_h16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(EMPTY_BAR(stage));
+          if (kb == p.num_kb - 1) umma_commit(TFULL_BAR(as));
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(TFULL_BAR(as));
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

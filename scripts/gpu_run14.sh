@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
+timeout 300 python scripts/prof_ops.py conv 1 > gpurun_out/prof_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm2_tcgen05 -c 3 -o gpurun_out/prof_conv_r01 python scripts/prof_ops.py conv 1 > gpurun_out/ncu_conv.log 2>&1
+echo "ncu conv exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt

@@ -32,7 +32,9 @@ if what in ("conv", "all"):
     x2 = rnd(B, 296, 296, 256); w2 = ops.pack_conv3x3_weight(rnd(128, 256, 3, 3, scale=(9 * 256) ** -0.5))
     bias2 = rnd(128, dtype=torch.float32)
     for _ in range(reps):
-        ops.conv3x3_h16(x1, w1, bias, None, None, 2)    # RCU conv at 148^2, F=256
+        ops.conv3x3_h16(x1, w1, bias, None, None, 2)    # RCU conv1 at 148^2, F=256
+        if what == "conv":
+            ops.conv3x3_h16(x1, w1, bias, x1, x1, 0, want_relu=True)  # RCU conv2: two skip adds + dual output
         ops.conv3x3_h16(x2, w2, bias2, None, None, 0)   # output_conv1 at 296^2, 256 -> 128
 if what in ("attn", "all"):
     qkv = rnd(M, 3 * D)
