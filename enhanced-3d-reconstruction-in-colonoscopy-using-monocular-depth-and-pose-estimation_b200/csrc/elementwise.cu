@@ -179,6 +179,8 @@ int launch_im2col_s2(const h16* in, h16* A, int B, int H, int W, int C, cudaStre
 // Bilinear resize, align_corners=True, NHWC h16 -> NHWC h16 (fp32 blend), 8 channels per thread.
 // src coordinate = dst * (in-1)/(out-1), exactly like F.interpolate(..., align_corners=True).
 // ----------------------------------------------------------------------------------------------
+static constexpr int BILINEAR_ROWS = 8;
+
 template <int FMT>
 __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restrict__ in, h16* __restrict__ out, int Hi, int Wi,
                                                             int Ho, int Wo, int C, float sy, float sx) {
@@ -188,29 +190,39 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Wo * c8) return;
   const int xo = t / c8, cv = t - xo * c8;
-  const int yo = blockIdx.y, b = blockIdx.z;
-  const float fy = sy * yo, fx = sx * xo;
-  const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
-  const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
-  const float wy = fy - (float)y0, wx = fx - (float)x0;
+  const int b = blockIdx.z;
+  const float fx = sx * xo;
+  const int x0 = min((int)fx, Wi - 1);
+  const int x1 = min(x0 + 1, Wi - 1);
+  const float wx = fx - (float)x0;
   const h16* base = in + (long long)b * Hi * Wi * C;
-  const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
-  const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
-  const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
-  const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
-  const uint32_t* a = &p00.x;
-  const uint32_t* bq = &p01.x;
-  const uint32_t* c = &p10.x;
-  const uint32_t* d = &p11.x;
-  uint4 o;
-  uint32_t* ow = &o.x;
-  const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+  // BILINEAR_ROWS output rows per thread: enough work per block to stay off the block-launch-rate limit
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 fa = unpack2<FMT>(a[k]), fb = unpack2<FMT>(bq[k]), fc = unpack2<FMT>(c[k]), fd = unpack2<FMT>(d[k]);
-    ow[k] = pack2<FMT>(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  for (int rr = 0; rr < BILINEAR_ROWS; ++rr) {
+    const int yo = blockIdx.y * BILINEAR_ROWS + rr;
+    if (yo >= Ho) break;
+    const float fy = sy * yo;
+    const int y0 = min((int)fy, Hi - 1);
+    const int y1 = min(y0 + 1, Hi - 1);
+    const float wy = fy - (float)y0;
+    const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
+    const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
+    const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
+    const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
+    const uint32_t* a = &p00.x;
+    const uint32_t* bq = &p01.x;
+    const uint32_t* c = &p10.x;
+    const uint32_t* d = &p11.x;
+    uint4 o;
+    uint32_t* ow = &o.x;
+    const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack2<FMT>(a[k]), fb = unpack2<FMT>(bq[k]), fc = unpack2<FMT>(c[k]), fd = unpack2<FMT>(d[k]);
+      ow[k] = pack2<FMT>(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    }
+    __stcs(reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Wo + xo) * C) + cv, o);
   }
-  __stcs(reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Wo + xo) * C) + cv, o);
 }
 
 int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int fmt, cudaStream_t stream) {
@@ -219,7 +231,7 @@ int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho,
   const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
-  dim3 grid((unsigned)((Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)B);
+  dim3 grid((unsigned)((Wo * (C / 8) + 255) / 256), (unsigned)((Ho + BILINEAR_ROWS - 1) / BILINEAR_ROWS), (unsigned)B);
   ProfScope ps(PC_RESAMPLE, 0.0, 2.0 * C * ((double)B * Hi * Wi + (double)B * Ho * Wo), stream);
   if (fmt == FMT_BF16) bilinear_nhwc_kernel<FMT_BF16><<<grid, 256, 0, stream>>>(in, out, Hi, Wi, Ho, Wo, C, sy, sx);
   else bilinear_nhwc_kernel<FMT_F16><<<grid, 256, 0, stream>>>(in, out, Hi, Wi, Ho, Wo, C, sy, sx);
