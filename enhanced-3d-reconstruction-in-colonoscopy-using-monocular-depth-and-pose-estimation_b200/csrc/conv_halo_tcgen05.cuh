@@ -26,9 +26,10 @@ struct ConvHaloCfg {
   static constexpr int A_STAGES = 2;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;     // this CTA's half of one tap's weight tile
   static constexpr int B_STAGES = BN == 256 ? 5 : 8;
-  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARPS = BN >= 128 ? 8 : 4;    // N = 32 (depth head): one warp per TMEM lane quadrant holds the whole row
+  static constexpr int HN = BN / (EPI_WARPS / 4);        // accumulator columns drained per epilogue warp
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * ::dav2::STG_ROW_BYTES;
-  static constexpr int VEC_BYTES = EPI_WARPS * (BN / 2) * 4;
+  static constexpr int VEC_BYTES = EPI_WARPS * HN * 4;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -41,13 +42,13 @@ __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint3
   return make_sw128_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
 }
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvHaloCfg<BN>::THREADS, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p, const int bo_mode) {
   using Cfg = ConvHaloCfg<BN>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
-  constexpr int MODE = GM_CONV_BF16;
+  static_assert(MODE == GM_CONV_BF16 || (MODE == GM_CONV_HEAD && BN == 32), "conv modes only");
   extern __shared__ uint8_t smem_raw[];
 
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -168,7 +169,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 2) {
     // ================================ epilogue (both CTAs, own 128 pixels) ===================
     const int q = warp & 3;
-    constexpr int HN = BN / 2;
+    constexpr int HN = Cfg::HN;
     const int col0 = ((warp - 2) >> 2) * HN;
     const uint32_t stg = staging + (uint32_t)(warp - 2) * 32u * STG_ROW_BYTES;
     const uint32_t vec = vecs + (uint32_t)(warp - 2) * (HN * 4);
@@ -184,11 +185,14 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       g.y0 = ty * Cfg::TH;
       g.x0 = (r - ty * p.tiles_x) * Cfg::TW;
       const bool tile_valid = g.tm < p.tiles_m;
-      epi_fill_bias<HN, MODE>(p, vec, lane, tn * BN + col0);
+      if constexpr (MODE != GM_CONV_HEAD) epi_fill_bias<HN, MODE>(p, vec, lane, tn * BN + col0);
       mbar_wait(TFULL_BAR(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + col0);
-      if (tile_valid) epi_tile_dispatch<HN, MODE>(p, t_row, stg, vec, lane, q, g, tn * BN + col0);
+      if (tile_valid) {
+        if constexpr (MODE == GM_CONV_HEAD) epi_tile_head(p, t_row, lane, q, g);
+        else epi_tile_dispatch<HN, MODE>(p, t_row, stg, vec, lane, q, g, tn * BN + col0);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -217,7 +221,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // Host launcher (gemm.cu).  tmA: NHWC map with box {64, 16, 18, 1}; tmB box rows bn/2; p.tw = 8, p.th = 16.
-int launch_conv_halo(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream);
+int launch_conv_halo(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream);
 bool conv_halo_eligible(int bn, int mode, int tiles_m);
 
 }  // namespace dav2

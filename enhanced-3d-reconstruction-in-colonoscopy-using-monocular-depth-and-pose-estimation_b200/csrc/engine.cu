@@ -365,7 +365,7 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   p.tiles_n = (Cout + bn - 1) / bn;
   if (p.ldo == 0) p.ldo = Cout;
   ProfScope ps2(PC_CONV, 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 2.0 * ((double)B * H * W * (Cin + Cout) + 9.0 * Cin * Cout), stream);
-  if (halo) return launch_conv_halo(bn, tmA, tmB, p, stream);
+  if (halo) return launch_conv_halo(bn, mode, tmA, tmB, p, stream);
   if (two_cta) return launch_gemm2(bn, mode, tmA, tmB, p, stream);
   return launch_gemm(bn, mode, tmA, tmB, p, stream);
 }

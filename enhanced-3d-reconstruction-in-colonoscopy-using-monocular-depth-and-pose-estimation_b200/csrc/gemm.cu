@@ -108,36 +108,40 @@ static int env_flag(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int BN>
+template <int BN, int MODE>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<BN>;
   static bool configured = false;
   static int bo_mode = 0;
   if (!configured) {
-    DAV2_CUDA_OK(cudaFuncSetAttribute(conv_halo_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DAV2_CUDA_OK(cudaFuncSetAttribute(conv_halo_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     bo_mode = env_flag("DAV2_HALO_BO", 0);
     configured = true;
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
-  const int max_pairs = sm_count() / 2;
+  // the N=32 head variant needs ~110 KB smem and 64 TMEM columns: two CTA pairs fit per TPC
+  const int max_pairs = (sm_count() / 2) * (Cfg::SMEM_BYTES <= 112 * 1024 ? 2 : 1);
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  conv_halo_tcgen05_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, bo_mode);
+  conv_halo_tcgen05_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, bo_mode);
   DAV2_LAUNCH_OK();
   return 0;
 }
 
-int launch_conv_halo(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  if (bn == 256) return launch_halo_t<256>(tmA, tmB, p, stream);
-  if (bn == 128) return launch_halo_t<128>(tmA, tmB, p, stream);
-  set_last_error("launch_conv_halo: unsupported bn=%d", bn);
+int launch_conv_halo(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  if (mode == GM_CONV_HEAD && bn == 32) return launch_halo_t<32, GM_CONV_HEAD>(tmA, tmB, p, stream);
+  if (mode == GM_CONV_BF16 && bn == 256) return launch_halo_t<256, GM_CONV_BF16>(tmA, tmB, p, stream);
+  if (mode == GM_CONV_BF16 && bn == 128) return launch_halo_t<128, GM_CONV_BF16>(tmA, tmB, p, stream);
+  set_last_error("launch_conv_halo: unsupported bn=%d mode=%d", bn, mode);
   return -3;
 }
 
 bool conv_halo_eligible(int bn, int mode, int tiles_m) {
   static int on = -1;  // DAV2_CONV_HALO=0 falls back to the per-tap box loads
   if (on < 0) on = env_flag("DAV2_CONV_HALO", 1);
-  return on == 1 && mode == GM_CONV_BF16 && (bn == 128 || bn == 256) && tiles_m >= 2 && gemm2_eligible(bn, mode, tiles_m);
+  if (on != 1 || tiles_m < 2) return false;
+  if (mode == GM_CONV_HEAD) return bn == 32 && env_flag("DAV2_GEMM2", 1) == 1;
+  return mode == GM_CONV_BF16 && (bn == 128 || bn == 256) && gemm2_eligible(bn, mode, tiles_m);
 }
 
 bool gemm2_eligible(int bn, int mode, int tiles_m) {
