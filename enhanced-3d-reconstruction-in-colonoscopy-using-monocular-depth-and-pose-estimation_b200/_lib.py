@@ -40,6 +40,10 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_depth_metrics": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
     "dav2_compose_poses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dav2_pose_create": (c_int, [C.POINTER(c_void_p), c_int]),
+    "dav2_pose_destroy": (None, [c_void_p]),
+    "dav2_pose_set_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, C.POINTER(c_i64), c_int]),
+    "dav2_pose_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dav2_linear_h16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dav2_linear_resid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dav2_conv3x3_h16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,9 +1,14 @@
 // extern "C" surface of libdav2_b200.so (declared in include/dav2_b200.h).
 #include <new>
 
-#include "engine.cuh"
+#include "posenet.cuh"
 
 using namespace dav2;
+
+struct dav2_pose {
+  PoseModel impl;
+  explicit dav2_pose(int precision) : impl(precision) {}
+};
 
 struct dav2_model {
   Model impl;
@@ -164,6 +169,24 @@ int dav2_bilinear_nhwc_h16(const void* in, void* out, int32_t B, int32_t Hi, int
   if (int rc = require_sm100()) return rc;
   DAV2_CHECK(in && out, "dav2_bilinear_nhwc_h16: null pointer");
   return launch_bilinear_nhwc((const h16*)in, (h16*)out, B, Hi, Wi, Ho, Wo, C, fmt, S(stream));
+}
+
+int dav2_pose_create(dav2_pose** out, int32_t precision) {
+  DAV2_CHECK(out && (precision == 0 || precision == 1), "dav2_pose_create: bad argument");
+  if (int rc = require_sm100()) return rc;
+  dav2_pose* m = new (std::nothrow) dav2_pose(precision);
+  DAV2_CHECK(m != nullptr, "dav2_pose_create: out of host memory");
+  *out = m;
+  return 0;
+}
+void dav2_pose_destroy(dav2_pose* m) { delete m; }
+int dav2_pose_set_weight(dav2_pose* m, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+  DAV2_CHECK(m, "null pose model");
+  return m->impl.set_weight(key, data, shape, ndim);
+}
+int dav2_pose_forward(dav2_pose* m, const float* x, int32_t B, int32_t H, int32_t W, float* pose7, void* stream) {
+  DAV2_CHECK(m, "null pose model");
+  return m->impl.forward(x, B, H, W, pose7, S(stream));
 }
 
 const char* dav2_last_error(void) { return get_last_error(); }

@@ -105,6 +105,19 @@ int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW
  * [N+1,12] = rows of [R|t] with R = Rotation.from_quat(q).as_matrix() (depth_to_pointcloud.py:168-173). */
 int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* abs7, double* T12, void* stream);
 
+/* PoseEstimationNet(in_channels=8).forward (pose_estimation_model.py:35-105): ResNet-18 with an 8-channel stem on
+ * stacked frame pairs [rgb1, d1, rgb2, d2] (data_processing/pose_estimation.py:229-243) -> fc 256 -> MLP -> 7
+ * = [t(3) | q xyzw(4)], eval semantics (BatchNorm running statistics, Dropout = identity).
+ * dav2_pose_set_weight takes HOST fp32 tensors with BatchNorm ALREADY FOLDED by the host layer:
+ *   "<conv>.weight" [Cout,Cin,k,k] and "<conv>.bias" [Cout] for conv1, layer{1..4}.{0,1}.conv{1,2},
+ *   layer{2..4}.0.downsample; "fc.weight" [256,512], "fc.bias"; "head.{0,1,2}.weight/bias" (the three Linear layers).
+ * dav2_pose_forward: x device fp32 [B,8,H,W] -> pose7 device fp32 [B,7]. */
+typedef struct dav2_pose dav2_pose;
+int dav2_pose_create(dav2_pose** out, int32_t precision);
+void dav2_pose_destroy(dav2_pose* m);
+int dav2_pose_set_weight(dav2_pose* m, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+int dav2_pose_forward(dav2_pose* m, const float* x, int32_t B, int32_t H, int32_t W, float* pose7, void* stream);
+
 /* Operator-level entry points (unit parity tests + reuse).  "h16" operands are 16-bit device tensors whose
  * numeric format is given by `fmt` (0 = fp16, 1 = bf16); accumulation is fp32.
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias)    A, W, C h16 row-major; bias fp32 or NULL; act 0/1(GELU)/2(ReLU) */
