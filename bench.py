@@ -200,6 +200,9 @@ def main():
     weights.randomize_(model, seed=0)
     cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     model = model.to(dev).eval()
+    weights.calibrate_(model, dev)  # spread the synthetic depth over (0, max_depth) instead of saturating the sigmoid
+    if cpu_sd is not None:
+        cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
 
     # device-resident inputs for `value`; distinct frames per rank (weak scaling)
     x_dev = synth_frames(B, S, S, dev, 1234 + rank)

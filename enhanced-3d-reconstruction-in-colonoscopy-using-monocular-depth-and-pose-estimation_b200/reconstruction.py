@@ -1,0 +1,74 @@
+"""Full reconstruction pass (BASELINE config 4): depth for every frame, relative poses for every consecutive
+pair, the pose chain, and world-frame back-projection -- the composition of reference stages
+(run.py / depth_to_pointcloud.py / pose_estimation_model.py / eval/evaluation.py) that the reference never wires
+together itself.
+
+Sharding: rank r owns the contiguous frames [a, b).  Pair i = (frame i, frame i+1) belongs to the
+rank that owns frame i, so a rank needs ONE halo frame (b) whose depth it recomputes locally instead of
+exchanging it.  The chain itself is 28 bytes per pair: relative poses are all-gathered and every rank composes the
+whole trajectory redundantly."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import evaluation, ops, sharding
+from .pose_estimation_model import stack_pairs
+
+
+def calculate_scale_factor(pred_rel_poses: torch.Tensor, gt_rel_poses: torch.Tensor) -> torch.Tensor:
+    """eval/evaluation.py:257-276: sum(pred_t . gt_t) / sum(pred_t . pred_t)."""
+    pt, gt = pred_rel_poses[:, :3], gt_rel_poses[:, :3]
+    return torch.sum(pt * gt) / torch.sum(pt * pt)
+
+
+@torch.no_grad()
+def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float | torch.Tensor = 1.0,
+                batch: int = 16, depth_for_pose_scale: float = 1.0, initial_pose: Optional[torch.Tensor] = None,
+                rank: int = 0, world: int = 1, group=None):
+    """frames: [N,3,H,W] normalised RGB of ONE video (every rank passes the same tensor or at least its shard + halo).
+
+    Returns dict(depth [n,H,W], rel [N-1,7] (scaled), abs [N,7], T12 [N,12], xyz [n,H*W,3], valid [n,H*W], counts [n],
+    frame_range (a, b)) for this rank's frames; gather clouds with ``sharding.gather_clouds`` when shards are equal."""
+    N, _, H, W = frames.shape
+    a, b = sharding.frame_range(N, rank, world)
+    hi = min(b + 1, N)  # halo frame for the last local pair
+    dev = next(depth_model.parameters()).device
+    depth = torch.empty(hi - a, H, W, dtype=torch.float32, device=dev)
+    for s in range(a, hi, batch):
+        e = min(s + batch, hi)
+        depth[s - a:e - a] = depth_model(frames[s:e].to(dev))
+    # relative poses of the local pairs (i, i+1), i in [a, min(b, N-1))
+    n_pairs = max(min(b, N - 1) - a, 0)
+    rel_local = torch.zeros(n_pairs, 7, dtype=torch.float32, device=dev)
+    if n_pairs:
+        rgb = frames[a:a + n_pairs + 1].to(dev)
+        d = depth[:n_pairs + 1, None] * depth_for_pose_scale
+        pairs = stack_pairs(rgb, d)
+        for s in range(0, n_pairs, batch):
+            rel_local[s:s + batch] = pose_model(pairs[s:s + batch])
+    # trajectory: gather the (tiny) relative poses, compose redundantly on every rank
+    if world > 1:
+        import torch.distributed as dist
+        counts = [max(min(sharding.frame_range(N, r, world)[1], N - 1) - sharding.frame_range(N, r, world)[0], 0) for r in range(world)]
+        parts = [torch.zeros(c, 7, dtype=torch.float32, device=dev) for c in counts]
+        dist.all_gather(parts, rel_local, group=group) if len(set(counts)) == 1 else _all_gather_ragged(parts, rel_local, rank, group)
+        rel = torch.cat(parts)
+    else:
+        rel = rel_local
+    rel = rel.clone()
+    rel[:, :3] *= scale  # the network predicts unit translation directions (data_processing/pose_estimation.py:256-258)
+    abs7, T12 = ops.compose_poses(rel.contiguous(), initial_pose, want_T12=True)
+    xyz, valid, counts_v = ops.backproject(depth[:b - a].contiguous(), k4, T12[a:b].contiguous())
+    return {"depth": depth[:b - a], "rel": rel, "abs": abs7, "T12": T12, "xyz": xyz, "valid": valid, "counts": counts_v,
+            "frame_range": (a, b)}
+
+
+def _all_gather_ragged(parts, mine, rank, group):
+    import torch.distributed as dist
+    for r, buf in enumerate(parts):
+        if r == rank:
+            buf.copy_(mine)
+        if buf.numel():
+            dist.broadcast(buf, src=r, group=group)

@@ -38,3 +38,34 @@ def randomize_(model, seed: int = 0):
     w.mul_(2.0 / max(float(w.norm()), 1e-6))
     model.mark_weights_changed()
     return model
+
+
+@torch.no_grad()
+def calibrate_(model, device="cuda", target_std=(3.0, 7.0), max_iter=12):
+    """Rescale the last 1x1 conv ON THE GPU until the depth map is spread over (0, max_depth) without
+    saturating: >15 % of pixels pinned within 2.5 % of either end -> halve the logit scale; depth std
+    below the target -> grow it.  Uses the engine itself (no CPU model exists in the product)."""
+    g = torch.Generator().manual_seed(4242)
+    u = torch.rand(2, 3, 98, 98, generator=g)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((u - mean) / std).to(device)
+    model.to(device)
+    w = model.depth_head.scratch.output_conv2[2].weight
+    model.depth_head.scratch.output_conv2[2].bias.zero_()
+    md = float(model.max_depth)
+    for _ in range(max_iter):
+        model.mark_weights_changed()
+        d = model(x)
+        sat = float(((d < 0.025 * md) | (d > 0.975 * md)).float().mean())
+        sd = float(d.std())
+        if sat > 0.15:
+            w.mul_(0.5)
+        elif sd < target_std[0] * md / 20.0:
+            w.mul_(1.6)
+        elif sd > target_std[1] * md / 20.0:
+            w.mul_(0.75)
+        else:
+            break
+    model.mark_weights_changed()
+    return model

@@ -71,3 +71,35 @@ def test_pose_net_contract():
     assert tuple(net.backbone.conv1.weight.shape) == (64, 8, 7, 7)
     with pytest.raises(Dav2Error):
         net.eval()(torch.zeros(1, 8, 64, 64))  # CPU tensor: no fallback
+
+
+def test_reconstruct_sharded_equals_single():
+    """Full pass on 6 frames: 2 emulated ranks (run one after the other, relative poses exchanged by hand) must
+    reproduce the single-rank trajectory and clouds -- the halo frame makes pair i local to the owner of frame i."""
+    from dav2_b200 import reconstruction, weights
+    from dav2_b200.dpt import MODEL_CONFIGS, DepthAnythingV2
+    _, pose = _build(seed=1)
+    depth_model = DepthAnythingV2(**MODEL_CONFIGS["vits"])
+    weights.randomize_(depth_model, seed=2)
+    depth_model = weights.calibrate_(depth_model.cuda().eval())
+    probe = depth_model(torch.randn(1, 3, 70, 98, generator=torch.Generator().manual_seed(1)).cuda())
+    assert 1.0 < float(probe.std()) < 9.0  # calibrated: neither flat nor saturated
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randn(6, 3, 70, 98, generator=g)
+    k4 = geo.scale_intrinsics(geo.SIMCOL_K_475, 475, 98)
+    one = reconstruction.reconstruct(frames, depth_model, pose, k4, scale=0.02, batch=4)
+    assert one["abs"].shape == (6, 7) and one["xyz"].shape == (6, 70 * 98, 3)
+    np.testing.assert_allclose(one["abs"].cpu().numpy(), geo.compose_poses(one["rel"].cpu().numpy()), rtol=1e-4, atol=1e-6)
+    # emulate 2 ranks: local pair poses of each shard must equal the corresponding slice of the single run
+    rel_parts = []
+    for r in range(2):
+        a, b = 3 * r, 3 * r + 3
+        hi = min(b + 1, 6)
+        sub = reconstruction.reconstruct(frames[a:hi], depth_model, pose, k4, scale=0.02, batch=4)
+        n_pairs = min(b, 5) - a
+        rel_parts.append(sub["rel"][:n_pairs])
+        assert float((sub["depth"][:b - a] - one["depth"][a:b]).abs().max() / one["depth"].abs().max()) < 1e-2
+    rel = torch.cat(rel_parts)
+    assert float((rel - one["rel"]).abs().max()) < 2e-2 * float(one["rel"].abs().max()) + 1e-4
+    s = reconstruction.calculate_scale_factor(one["rel"], one["rel"] * 2.0)
+    assert abs(float(s) - 2.0) < 1e-5
