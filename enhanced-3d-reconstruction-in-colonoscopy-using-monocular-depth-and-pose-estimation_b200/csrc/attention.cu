@@ -169,10 +169,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         for (int i = 0; i < 128; ++i)
           if (i >= nvalid) sreg[i] = 0xff800000u;  // -inf
       }
-      float mx = __uint_as_float(sreg[0]);
+      // four independent chains (a single running max / sum is a 64-deep dependent chain: 'wait' stalls in ncu)
+      float mx0 = __uint_as_float(sreg[0]), mx1 = __uint_as_float(sreg[1]), mx2 = __uint_as_float(sreg[2]),
+            mx3 = __uint_as_float(sreg[3]);
 #pragma unroll
-      for (int i = 1; i < 127; i += 2) mx = fmax3(mx, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
-      mx = fmaxf(mx, __uint_as_float(sreg[127]));
+      for (int i = 4; i < 124; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sreg[i + 2]), __uint_as_float(sreg[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sreg[i + 4]), __uint_as_float(sreg[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sreg[i + 6]), __uint_as_float(sreg[i + 7]));
+      }
+      mx0 = fmax3(mx0, __uint_as_float(sreg[124]), __uint_as_float(sreg[125]));
+      mx1 = fmax3(mx1, __uint_as_float(sreg[126]), __uint_as_float(sreg[127]));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       bool o_waited = false;
       if (j == 0) {
         m_ref = mx;
@@ -200,15 +209,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         }
       }
       const float mscaled = m_ref * LOG2E;
-      float rowsum = 0.f;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 64; i += 2) {
         const float e0 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i]), LOG2E, -mscaled));
         const float e1 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 1]), LOG2E, -mscaled));
-        rowsum += e0 + e1;
-        sreg[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);  // in place: slot i <= 2i is already consumed
+        const float e2 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 2]), LOG2E, -mscaled));
+        const float e3 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 3]), LOG2E, -mscaled));
+        rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
+        // in place: slots i, i+1 <= 2i are already consumed
+        sreg[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
+        sreg[i + 1] = FP16 ? pack2<FMT_F16>(e2, e3) : pack2<FMT_BF16>(e2, e3);
       }
-      l += rowsum;
+      l += (rs0 + rs1) + (rs2 + rs3);
       if (j > 0 && !o_waited) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P buffer
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
