@@ -79,3 +79,134 @@ def poses_to_transforms(abs_poses: torch.Tensor) -> torch.Tensor:
         _, T = ops.compose_poses(zero_rel, abs_poses[i], want_T12=True)
         out.append(T[0])
     return torch.stack(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose metrics (eval/evaluation.py:63-254) -- trajectory-level scalars over N x 7 arrays: host numpy, like the
+# reference; the pose CHAIN inside evaluate_trajectory runs on the GPU kernel when the inputs are CUDA tensors.
+# ------------------------------------------------------------------------------------------------
+def _np(a):
+    import numpy as np
+    return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+
+
+def _quat_to_matrix(q):
+    import numpy as np
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def quaternion_distance(q1, q2):
+    """eval/evaluation.py:63-82: geodesic angle in degrees."""
+    import numpy as np
+    q1, q2 = _np(q1).astype(np.float64), _np(q2).astype(np.float64)
+    q1, q2 = q1 / np.linalg.norm(q1), q2 / np.linalg.norm(q2)
+    return float(np.degrees(2 * np.arccos(np.clip(np.abs(np.dot(q1, q2)), -1.0, 1.0))))
+
+
+def compute_ate(gt_trans, pred_trans):
+    """eval/evaluation.py:85-99."""
+    import numpy as np
+    e = np.linalg.norm(_np(gt_trans) - _np(pred_trans), axis=1)
+    return np.sqrt(np.mean(e ** 2))
+
+
+def compute_rte(gt_trans, pred_trans):
+    """eval/evaluation.py:102-120."""
+    import numpy as np
+    return np.mean(np.linalg.norm(np.diff(_np(gt_trans), axis=0) - np.diff(_np(pred_trans), axis=0), axis=1))
+
+
+def compute_rot_error(gt_rots, pred_rots):
+    """eval/evaluation.py:123-161: mean angle of R_gt^T R_pred in degrees; zero predicted quaternion -> identity."""
+    import numpy as np
+    errs = []
+    for q_gt, q_pred in zip(_np(gt_rots).astype(np.float64), _np(pred_rots).astype(np.float64)):
+        if np.linalg.norm(q_pred) < 1e-8:
+            q_pred = np.array([0.0, 0.0, 0.0, 1.0])
+            logger.warning("Zero quaternion detected, using identity quaternion instead")
+        q_gt, q_pred = q_gt / np.linalg.norm(q_gt), q_pred / np.linalg.norm(q_pred)
+        r = _quat_to_matrix(q_gt).T @ _quat_to_matrix(q_pred)
+        errs.append(np.degrees(np.arccos(np.clip((np.trace(r) - 1) / 2, -1.0, 1.0))))
+    return np.mean(errs)
+
+
+def compute_pose_errors(pred_positions: torch.Tensor, gt_positions: torch.Tensor) -> dict:
+    """eval/evaluation.py:164-208."""
+    import numpy as np
+    p, g = _np(pred_positions).copy(), _np(gt_positions).copy()
+    pq, gq = p[:, 3:], g[:, 3:]
+    pq = pq / np.maximum(np.linalg.norm(pq, axis=1, keepdims=True), 1e-8)
+    gq = gq / np.maximum(np.linalg.norm(gq, axis=1, keepdims=True), 1e-8)
+    pq[np.sum(gq * pq, axis=1) < 0] *= -1
+    return {"ate": torch.as_tensor(compute_ate(g[:, :3], p[:, :3])), "rte": torch.as_tensor(compute_rte(g[:, :3], p[:, :3])),
+            "rote": torch.as_tensor(compute_rot_error(gq, pq))}
+
+
+def calculate_scale_factor(pred_rel_poses, gt_rel_poses):
+    """eval/evaluation.py:257-276."""
+    pt, gt = pred_rel_poses[:, :3], gt_rel_poses[:, :3]
+    return torch.sum(pt * gt) / torch.sum(pt * pt)
+
+
+def evaluate_trajectory(pred_rel_poses: torch.Tensor, gt_rel_poses: torch.Tensor, initial_pose: Optional[torch.Tensor] = None):
+    """eval/evaluation.py:211-254: scale-align, compose both chains (GPU kernel), ATE / RTE / ROT."""
+    scale = calculate_scale_factor(pred_rel_poses, gt_rel_poses)
+    scaled = pred_rel_poses.clone()
+    scaled[:, :3] *= scale
+    dev = scaled.device if scaled.is_cuda else torch.device("cuda")
+    pred_abs = compose_poses(scaled.to(dev), None if initial_pose is None else initial_pose.to(dev))
+    gt_abs = compose_poses(gt_rel_poses.to(dev), None if initial_pose is None else initial_pose.to(dev))
+    return {"rte": compute_rte(scaled[:, :3], gt_rel_poses[:, :3]), "ate": compute_ate(gt_abs[:, :3], pred_abs[:, :3]),
+            "rote": compute_rot_error(gt_abs[:, 3:], pred_abs[:, 3:])}
+
+
+# ------------------------------------------------------------------------------------------------
+# Per-procedure aggregation of test_lightning.py:27-111 / :240-274 (host bookkeeping; no Lightning needed)
+# ------------------------------------------------------------------------------------------------
+class ProcedureMetricCollector:
+    """The reference appends the BATCH metric once per frame to the frame's procedure bucket
+    (test_lightning.py:76-109) and reports mean over procedures of per-procedure means (:244-274)."""
+
+    KEYS = ("l1", "abs_rel", "d1", "rmse")
+
+    def __init__(self):
+        from collections import defaultdict
+        self.metrics_by_procedure = defaultdict(list)
+
+    @staticmethod
+    def procedure_of(dataset_path: str, frame_id: str):
+        colon = None
+        for part in str(dataset_path).split("/"):
+            if part.startswith("SyntheticColon_"):
+                colon = part
+        proc = None
+        for tag in ("S", "B", "O"):
+            if tag in frame_id:
+                proc = f"Frames_{tag}{frame_id.split(tag)[1].split('_')[0]}"
+                break
+        return None if colon is None or proc is None else f"{colon}/{proc}"
+
+    def on_test_batch_end(self, outputs: dict, batch: dict):
+        if not all(k in outputs for k in self.KEYS):
+            raise ValueError("Missing expected keys in outputs")
+        m = {k: float(outputs[k]) for k in self.KEYS}
+        for ds, fid in zip(batch["dataset"], batch["id"]):
+            p = self.procedure_of(str(ds), str(fid))
+            if p is not None:
+                self.metrics_by_procedure[p].append(m)
+
+    def summary(self) -> dict:
+        import numpy as np
+        per, allm = {}, {k: [] for k in self.KEYS}
+        for proc, lst in self.metrics_by_procedure.items():
+            arr = np.array([[m[k] for k in self.KEYS] for m in lst])
+            mean = arr.mean(axis=0)
+            per[proc] = dict(zip(self.KEYS, mean.tolist()))
+            for k, v in zip(self.KEYS, mean):
+                allm[k].append(v)
+        overall = {k: {"mean": float(np.mean(v)) if v else float("nan"), "std": float(np.std(v)) if v else float("nan")}
+                   for k, v in allm.items()}
+        return {"per_procedure": per, "overall_metrics": overall}

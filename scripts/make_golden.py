@@ -101,5 +101,36 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
+def pose_metric_fixtures():
+    """tests/golden/pose_metrics_small.npz: eval/evaluation.py:63-254 executed on a seeded synthetic trajectory."""
+    import sys
+    import numpy as np
+    import torch
+    from scipy.spatial.transform import Rotation as R
+    sys.path.insert(0, REF)
+    from eval import evaluation as ref
+    rng = np.random.default_rng(77)
+    N = 40
+
+    def rel(n, s):
+        t = rng.normal(0, s, size=(n, 3))
+        q = R.from_rotvec(np.deg2rad(rng.normal(0, 2.0, size=(n, 3)))).as_quat()
+        return np.concatenate([t, q], 1).astype(np.float32)
+
+    gt = rel(N, 0.01)
+    pred = gt.copy()
+    pred[:, :3] = pred[:, :3] / np.linalg.norm(pred[:, :3], axis=1, keepdims=True) + rng.normal(0, 0.05, size=(N, 3)).astype(np.float32)
+    pred[:, 3:] += rng.normal(0, 0.01, size=(N, 4)).astype(np.float32)
+    pred[5, 3:] = 0
+    traj = ref.evaluate_trajectory(torch.from_numpy(pred), torch.from_numpy(gt))
+    absg, absp = ref.compose_poses(torch.from_numpy(gt)), ref.compose_poses(torch.from_numpy(pred))
+    pe = ref.compute_pose_errors(absp, absg)
+    np.savez_compressed(os.path.join(OUT, "pose_metrics_small.npz"), gt=gt, pred=pred,
+                        traj=np.array([float(traj["rte"]), float(traj["ate"]), float(traj["rote"])]),
+                        pose_errors=np.array([float(pe["ate"]), float(pe["rte"]), float(pe["rote"])]),
+                        qdist=np.array([ref.quaternion_distance(gt[0, 3:], pred[0, 3:])]))
+
+
 if __name__ == "__main__":
     main()
+    pose_metric_fixtures()
