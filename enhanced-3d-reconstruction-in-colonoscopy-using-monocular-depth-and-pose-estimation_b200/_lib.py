@@ -36,6 +36,7 @@ SIGNATURES = {
     "dav2_debug_buffer": (c_int, [c_void_p, C.c_char_p, C.POINTER(c_void_p), C.POINTER(c_i64)]),
     "dav2_debug_read": (c_int, [c_void_p, C.c_char_p, c_void_p, c_i64, c_void_p]),
     "dav2_resize_depth": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dav2_preprocess_bgr_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dav2_backproject": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_depth_metrics": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),

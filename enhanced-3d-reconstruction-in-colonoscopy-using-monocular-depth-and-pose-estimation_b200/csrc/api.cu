@@ -87,6 +87,11 @@ int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float*
   return launch_bilinear_f32(in, out, B, Hi, Wi, Ho, Wo, S(stream));
 }
 
+int dav2_preprocess_bgr_u8(const uint8_t* img, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_preprocess_bgr(img, H, W, out, nh, nw, S(stream));
+}
+
 int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
                      const double* T12, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
                      int32_t* counts, void* stream) {

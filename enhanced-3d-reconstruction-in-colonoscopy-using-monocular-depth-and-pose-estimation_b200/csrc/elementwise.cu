@@ -274,3 +274,76 @@ int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int 
 }
 
 }  // namespace dav2
+
+namespace dav2 {
+
+// ----------------------------------------------------------------------------------------------
+// Upstream image2tensor on the GPU (external dpt.py / util/transform.py; reference call run.py:233-234):
+// BGR uint8 [H,W,3] -> RGB/255 -> cv2.resize(INTER_CUBIC) to (nh, nw) -> (x - mean)/std -> fp32 CHW.
+// OpenCV's bicubic: src = (dst + 0.5) * scale - 0.5, taps floor(src)-1 .. +2 with replicated borders,
+// A = -0.75, fp32 coefficient tables, separable, fp64 pixels (the reference divides by 255.0 in fp64).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+  c[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+__global__ void __launch_bounds__(256) preprocess_bgr_kernel(const uint8_t* __restrict__ img, int H, int W, float* __restrict__ out,
+                                                             int nh, int nw, double sy, double sx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nh * nw) return;
+  const int dy = t / nw, dx = t - dy * nw;
+  float cy[4], cx[4];
+  int iy[4], ix[4];
+  if (nh == H) {  // cv2.resize with identical size is a copy
+    cy[0] = 0.f; cy[1] = 1.f; cy[2] = 0.f; cy[3] = 0.f;
+    for (int k = 0; k < 4; ++k) iy[k] = min(max(dy - 1 + k, 0), H - 1);
+  } else {
+    float fy = (float)((dy + 0.5) * sy - 0.5);
+    const int s = (int)floorf(fy);
+    fy -= (float)s;
+    cubic_coeffs(fy, cy);
+    for (int k = 0; k < 4; ++k) iy[k] = min(max(s - 1 + k, 0), H - 1);
+  }
+  if (nw == W) {
+    cx[0] = 0.f; cx[1] = 1.f; cx[2] = 0.f; cx[3] = 0.f;
+    for (int k = 0; k < 4; ++k) ix[k] = min(max(dx - 1 + k, 0), W - 1);
+  } else {
+    float fx = (float)((dx + 0.5) * sx - 0.5);
+    const int s = (int)floorf(fx);
+    fx -= (float)s;
+    cubic_coeffs(fx, cx);
+    for (int k = 0; k < 4; ++k) ix[k] = min(max(s - 1 + k, 0), W - 1);
+  }
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int r = 0; r < 4; ++r) {
+    double row[3] = {0.0, 0.0, 0.0};
+    const uint8_t* line = img + (long long)iy[r] * W * 3;
+    for (int k = 0; k < 4; ++k) {
+      const uint8_t* px = line + ix[k] * 3;
+      row[0] += (double)cx[k] * ((double)px[2] / 255.0);  // R
+      row[1] += (double)cx[k] * ((double)px[1] / 255.0);  // G
+      row[2] += (double)cx[k] * ((double)px[0] / 255.0);  // B
+    }
+    acc[0] += (double)cy[r] * row[0];
+    acc[1] += (double)cy[r] * row[1];
+    acc[2] += (double)cy[r] * row[2];
+  }
+  const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+  const long long plane = (long long)nh * nw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[c * plane + t] = (float)((acc[c] - mean[c]) / stdv[c]);
+}
+
+int launch_preprocess_bgr(const uint8_t* img, int H, int W, float* out, int nh, int nw, cudaStream_t stream) {
+  DAV2_CHECK(img && out && H > 0 && W > 0 && nh > 0 && nw > 0, "preprocess: bad arguments");
+  ProfScope ps(PC_RESAMPLE, 0.0, (double)H * W * 3.0 + (double)nh * nw * 12.0, stream);
+  preprocess_bgr_kernel<<<(nh * nw + 255) / 256, 256, 0, stream>>>(img, H, W, out, nh, nw, (double)H / nh, (double)W / nw);
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace dav2

@@ -13,6 +13,8 @@ int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho,
 int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
 int launch_cast_bf16(const float* in, h16* out, long long n, cudaStream_t stream);
 
+int launch_preprocess_bgr(const uint8_t* img, int H, int W, float* out, int nh, int nw, cudaStream_t stream);
+
 // attention.cu
 int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo = 1024,
                      uint32_t v_sbo = 1024);

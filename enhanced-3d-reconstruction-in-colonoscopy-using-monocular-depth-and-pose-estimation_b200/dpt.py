@@ -210,11 +210,27 @@ class DepthAnythingV2(nn.Module):
 
     @torch.no_grad()
     def infer_image(self, raw_image: np.ndarray, input_size: int = 518) -> np.ndarray:
-        image, (h, w) = self.image2tensor(raw_image, input_size)
+        """run.py:234.  The uint8 frame (3 B/px) is uploaded and pre-processed ON the GPU (bicubic resize +
+        normalisation kernel), instead of building a 12 B/px float tensor with OpenCV on the host."""
         dev = next(self.parameters()).device
-        depth = self.forward(image.to(dev))
+        h, w = raw_image.shape[:2]
+        nh, nw = self.target_size(h, w, input_size)
+        raw = torch.from_numpy(np.ascontiguousarray(raw_image)).to(dev)
+        image = ops.preprocess_bgr_u8(raw, nh, nw)
+        depth = self.forward(image)
         depth = ops.resize_depth(depth, h, w)[0]
         return depth.cpu().numpy()
+
+    @staticmethod
+    def target_size(h: int, w: int, input_size: int = 518):
+        """Resize(keep_aspect_ratio, ensure_multiple_of=14, 'lower_bound') of upstream util/transform.py."""
+        scale = max(input_size / h, input_size / w)
+
+        def _mult(v):
+            y = int(np.round(v / 14) * 14)
+            return y if y >= input_size else int(np.ceil(v / 14) * 14)
+
+        return _mult(scale * h), _mult(scale * w)
 
     @staticmethod
     def image2tensor(raw_image: np.ndarray, input_size: int = 518):

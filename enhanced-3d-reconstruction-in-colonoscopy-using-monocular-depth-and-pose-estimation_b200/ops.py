@@ -174,3 +174,14 @@ def compose_poses(rel: torch.Tensor, init7: torch.Tensor | None = None, want_T12
     check(_lib.load().dav2_compose_poses(rel.data_ptr(), _ptr(init7), N, abs7.data_ptr(), _ptr(T12),
                                          current_stream_ptr(rel.device)), "dav2_compose_poses")
     return (abs7, T12) if want_T12 else abs7
+
+
+def preprocess_bgr_u8(img_u8: torch.Tensor, nh: int, nw: int) -> torch.Tensor:
+    """BGR uint8 [H,W,3] (device) -> normalised RGB fp32 [1,3,nh,nw] with OpenCV-compatible bicubic resize."""
+    require_cuda(img_u8, "img")
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3
+    H, W = img_u8.shape[:2]
+    out = torch.empty(1, 3, nh, nw, dtype=torch.float32, device=img_u8.device)
+    check(_lib.load().dav2_preprocess_bgr_u8(img_u8.data_ptr(), H, W, out.data_ptr(), nh, nw,
+                                             current_stream_ptr(img_u8.device)), "dav2_preprocess_bgr_u8")
+    return out

@@ -74,6 +74,11 @@ int dav2_debug_read(dav2_model* m, const char* name, void* dst, int64_t bytes, v
 int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float* out, int32_t Ho, int32_t Wo,
                       void* stream);
 
+/* Upstream image2tensor on the GPU (external dpt.py image2tensor, called through infer_image at run.py:233-234):
+ * img device u8 [H,W,3] BGR (cv2.imread layout) -> RGB/255 -> cv2.INTER_CUBIC resize to (nh, nw) -> ImageNet
+ * normalisation -> out device fp32 [3,nh,nw].  (nh, nw) = the lower-bound, multiple-of-14 size computed by the host. */
+int dav2_preprocess_bgr_u8(const uint8_t* img, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw, void* stream);
+
 /* Fused back-projection + SE(3) world transform + validity mask.
  * Replaces depth_to_pointcloud.py:218-239 (Open3D RGBD -> PointCloud.create_from_rgbd_image -> transform)
  * and the explicit formula at depth_to_pointcloud_dav2.py:300-313.

@@ -95,6 +95,20 @@ def test_infer_image_matches_oracle():
     assert np.abs(got - ref).max() / np.abs(ref).max() < DEPTH_TOL
 
 
+@pytest.mark.parametrize("h,w,size", [(95, 120, 140), (475, 475, 518), (140, 140, 140), (108, 135, 70)])
+def test_gpu_preprocess_matches_opencv(h, w, size):
+    """image2tensor on the GPU vs the upstream OpenCV path (cv2.INTER_CUBIC on the fp64 RGB/255 image)."""
+    from dav2_b200 import ops
+    from dav2_b200.dpt import DepthAnythingV2
+    rng = np.random.default_rng(h + w)
+    img = rng.integers(0, 255, size=(h, w, 3), dtype=np.uint8)
+    ref, _ = O.image2tensor(img, size)
+    nh, nw = DepthAnythingV2.target_size(h, w, size)
+    assert (nh, nw) == tuple(ref.shape[-2:])
+    got = ops.preprocess_bgr_u8(torch.from_numpy(img).cuda(), nh, nw).cpu()
+    assert float((got - ref).abs().max()) < 2e-5
+
+
 def test_cpu_input_is_rejected():
     from dav2_b200._lib import Dav2Error
     _, m = _build("vits")
