@@ -99,6 +99,12 @@ int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const 
   return launch_backproject(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, xyz, valid, counts, S(stream));
 }
 
+int dav2_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, int64_t n, double voxel_size, float* out_xyz,
+                          float* out_rgb, int64_t* out_count, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_voxel_downsample(xyz, rgb, valid, (long long)n, voxel_size, out_xyz, out_rgb, (long long*)out_count, S(stream));
+}
+
 int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float lo, float hi,
                        int32_t variant, int32_t per_frame, double* partials, void* stream) {
   if (int rc = require_sm100()) return rc;

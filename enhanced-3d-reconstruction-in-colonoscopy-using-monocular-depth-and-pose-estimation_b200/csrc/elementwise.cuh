@@ -15,6 +15,10 @@ int launch_cast_bf16(const float* in, h16* out, long long n, cudaStream_t stream
 
 int launch_preprocess_bgr(const uint8_t* img, int H, int W, float* out, int nh, int nw, cudaStream_t stream);
 
+// voxel.cu
+int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, long long n, double voxel, float* out_xyz,
+                            float* out_rgb, long long* out_count, cudaStream_t stream);
+
 // attention.cu
 int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo = 1024,
                      uint32_t v_sbo = 1024);

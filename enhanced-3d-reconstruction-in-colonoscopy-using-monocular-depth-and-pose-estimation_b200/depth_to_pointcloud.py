@@ -5,8 +5,8 @@ RGBD image (z = d/1000, z >= 3 -> 0), pinhole back-projection of z > 0 pixels, 4
 transform from the ground-truth pose.  Here ONE fused kernel (dav2_backproject) does
 back-projection + SE(3) + validity on the GPU; compaction / colour gather are torch indexing on
 the device.  ``PointCloud`` mimics the small part of ``o3d.geometry.PointCloud`` the script uses
-(``.points``, ``.colors``, ``.transform``, ``+=``).  Voxel down-sampling and Poisson meshing
-(:245-281, :357-362) are out of scope.
+(``.points``, ``.colors``, ``.transform``, ``+=``, ``.voxel_down_sample``).  Poisson meshing (:245-281, :361-362) is out of scope
+(a global sparse solve inside Open3D).
 """
 from __future__ import annotations
 
@@ -72,6 +72,16 @@ class PointCloud:
         self._p += other._p
         self._c += other._c
         return self
+
+    def voxel_down_sample(self, voxel_size: float) -> "PointCloud":
+        """o3d PointCloud.voxel_down_sample (depth_to_pointcloud.py:357-359) on the GPU (dav2_voxel_downsample)."""
+        p, c = self._cat()
+        if p is None or p.shape[0] == 0:
+            return PointCloud()
+        if c is not None and c.shape[0] != p.shape[0]:
+            c = None
+        q, qc = ops.voxel_downsample(p, voxel_size, c)
+        return PointCloud(q, qc)
 
     def transform(self, T):
         p, _ = self._cat()
@@ -180,11 +190,12 @@ def write_ply(path: str, cloud: PointCloud) -> None:
 
 
 def main(depth_image_paths: list, color_image_paths: list, output_dir: str) -> PointCloud:
-    """depth_to_pointcloud.py:316-371 without the voxel down-sample / Poisson mesh (out of scope)."""
+    """depth_to_pointcloud.py:316-371 without the Poisson mesh (out of scope)."""
     combined = PointCloud()
     for frame_idx, (dp, cp) in enumerate(zip(depth_image_paths, color_image_paths)):
         cam, pos, rot = get_procedure_files(cp)
         combined += generate_point_cloud(dp, cp, cam, pos, rot, frame_idx)
+    combined = combined.voxel_down_sample(voxel_size=0.01)  # :357-359
     os.makedirs(output_dir, exist_ok=True)
     write_ply(f"{output_dir}/combined_point_cloud.ply", combined)
     return combined

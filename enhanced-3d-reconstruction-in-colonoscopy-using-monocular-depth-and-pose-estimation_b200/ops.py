@@ -148,6 +148,33 @@ def backproject(depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, dep
     return xyz, valid, counts
 
 
+def voxel_downsample(xyz: torch.Tensor, voxel_size: float, rgb: torch.Tensor | None = None,
+                     valid: torch.Tensor | None = None):
+    """Open3D-style voxel_down_sample: xyz fp32 [n,3] (+ rgb fp32 [n,3], valid u8 [n]) -> (xyz [m,3], rgb [m,3] | None),
+    one mean point per occupied voxel, ordered by voxel index.  One host sync (the voxel count)."""
+    require_cuda(xyz, "xyz")
+    assert xyz.dtype == torch.float32 and xyz.dim() == 2 and xyz.shape[1] == 3
+    if not voxel_size > 0.0:
+        raise ValueError("voxel_size <= 0.")  # Open3D's message
+    xyz = xyz.contiguous()
+    n, dev = xyz.shape[0], xyz.device
+    if rgb is not None:
+        rgb = rgb.to(device=dev, dtype=torch.float32).contiguous()
+        assert rgb.shape == xyz.shape
+    if valid is not None:
+        valid = valid.to(device=dev, dtype=torch.uint8).contiguous()
+        assert valid.numel() == n
+    out_xyz = torch.empty_like(xyz)
+    out_rgb = torch.empty_like(xyz) if rgb is not None else None
+    count = torch.empty(1, dtype=torch.int64, device=dev)
+    check(_lib.load().dav2_voxel_downsample(xyz.data_ptr(), _ptr(rgb), _ptr(valid), n, float(voxel_size), out_xyz.data_ptr(),
+                                            _ptr(out_rgb), count.data_ptr(), current_stream_ptr(dev)), "dav2_voxel_downsample")
+    m = int(count.item())
+    if m < 0:
+        raise RuntimeError("voxel_size is too small.")  # Open3D's message
+    return out_xyz[:m], (out_rgb[:m] if out_rgb is not None else None)
+
+
 def depth_metric_partials(pred: torch.Tensor, gt: torch.Tensor, lo: float, hi: float, variant: int,
                           per_frame: bool) -> torch.Tensor:
     """fp64 partial sums [B,8] or [8] (see include/dav2_b200.h) for pred/gt fp32 [B, ...]."""

@@ -93,6 +93,17 @@ int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const 
                      const double* T12, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
                      int32_t* counts, void* stream);
 
+/* Voxel-grid down-sample of a fused cloud: depth_to_pointcloud.py:357-359 (`combined.voxel_down_sample(voxel_size=0.01)`,
+ * i.e. Open3D PointCloud::VoxelDownSample): voxel index = floor((p - (min_bound - voxel/2)) / voxel) per axis, one output
+ * point per occupied voxel = the mean (accumulated in fp64) of its points, colours averaged the same way.
+ *   xyz    device fp32 [n,3];  rgb device fp32 [n,3] or NULL;  valid device u8 [n] or NULL (0 / non-finite -> dropped)
+ *   out_xyz device fp32 [n,3] (worst case), out_rgb device fp32 [n,3] or NULL; rows [0, *out_count) are written,
+ *   ordered by ascending (ix, iy, iz) (Open3D emits hash-map order: compare as sets)
+ *   out_count device i64 [1]: number of voxels, or -1 when the grid exceeds 2^21 cells on an axis
+ *   (Open3D's "voxel_size is too small" error).  n < 2^31. */
+int dav2_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, int64_t n, double voxel_size,
+                          float* out_xyz, float* out_rgb, int64_t* out_count, void* stream);
+
 /* Depth-metric partial sums (finalise on the host AFTER any cross-GPU sum).
  *   variant 0: evaluation.compute_errors on the batch-wide mask lo <= gt <= hi
  *              (eval/evaluation.py:16-60, lightning_model.py:304-313)

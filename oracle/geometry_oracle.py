@@ -18,6 +18,14 @@ Restates, citing the reference (paths relative to /root/reference):
                              quaternion_rotate_vector :427-485 (float32, sequential, xyzw, zero-norm
                              relative quaternion -> identity, q NOT normalised).
 
+* ``voxel_down_sample``      depth_to_pointcloud.py:357-359 -> Open3D ``PointCloud::VoxelDownSample`` (Open3D >=0.18,
+                             requirements.txt:10; cpp/open3d/geometry/PointCloud.cpp): voxel_min_bound =
+                             min_bound - voxel/2; index = floor((p - voxel_min_bound)/voxel) per axis; one
+                             output point per occupied voxel = mean (float64 accumulation) of its points and
+                             colours.  Open3D emits hash-map order; the oracle emits ascending (ix,iy,iz).
+                             Open3D is not installable here: "parity unpinned" by execution, pinned by the
+                             hand-computed case in tests/test_oracle_geometry_metrics.py.
+
 PINNING: quat_to_matrix is checked against scipy (installed); compose_poses against the reference's
 own ``eval.evaluation.compose_poses`` executed in the build container (fixtures in
 tests/golden/, generator scripts/make_golden.py).  Open3D itself is not installed anywhere we
@@ -142,3 +150,30 @@ def poses_to_T12(abs7) -> np.ndarray:
         T = make_transform(p[:3], p[3:])
         out[i] = T[:3, :4].reshape(-1)
     return out
+
+
+def voxel_down_sample(points, voxel_size: float, colors=None):
+    """points [n,3] (any float dtype; promoted to float64 like Open3D's Vector3d) -> (means [m,3], colour means | None,
+    voxel indices [m,3]) sorted by (ix, iy, iz)."""
+    if not voxel_size > 0.0:
+        raise ValueError("voxel_size <= 0.")
+    p = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    if p.shape[0] == 0:
+        return p, (None if colors is None else np.zeros((0, 3))), np.zeros((0, 3), dtype=np.int64)
+    vmin = p.min(axis=0) - 0.5 * voxel_size
+    vmax = p.max(axis=0) + 0.5 * voxel_size
+    if voxel_size * np.iinfo(np.int32).max < (vmax - vmin).max():
+        raise RuntimeError("voxel_size is too small.")
+    idx = np.floor((p - vmin) / voxel_size).astype(np.int64)
+    uniq, inv = np.unique(idx, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    cnt = np.bincount(inv, minlength=uniq.shape[0]).astype(np.float64)
+    acc = np.zeros((uniq.shape[0], 3))
+    np.add.at(acc, inv, p)  # sequential in index order, like the reference's loop
+    out_c = None
+    if colors is not None:
+        c = np.asarray(colors, dtype=np.float64).reshape(-1, 3)
+        accc = np.zeros((uniq.shape[0], 3))
+        np.add.at(accc, inv, c)
+        out_c = accc / cnt[:, None]
+    return acc / cnt[:, None], out_c, uniq

