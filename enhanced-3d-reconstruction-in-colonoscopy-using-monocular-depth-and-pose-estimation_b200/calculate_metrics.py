@@ -29,13 +29,8 @@ def calculate_metrics_batch(gt, pred, mask_invalid: bool = True, device="cuda"):
     """Per-frame metrics for [B,H,W] stacks in one launch -> list of dicts."""
     g, p = _to_dev(gt, device), _to_dev(pred, device)
     assert g.shape == p.shape and g.dim() == 3
-    part = ops.depth_metric_partials(p, g, 0.0, 0.0, 1 if mask_invalid else 2, True).cpu().numpy()
-    out = []
-    for row in part:
-        if not mask_invalid:  # variant 2 counts the 1.1 threshold; recompute is not needed by the reference path
-            raise NotImplementedError("mask_invalid=False is not used by the reference (calculate_metrics.py:78)")
-        out.append(finalize_calculate_metrics(row))
-    return out
+    part = ops.depth_metric_partials(p, g, 0.0, 0.0, 1 if mask_invalid else 3, True).cpu().numpy()
+    return [finalize_calculate_metrics(row) for row in part]
 
 
 def calculate_metrics(gt, pred, mask_invalid: bool = True, device="cuda") -> dict:

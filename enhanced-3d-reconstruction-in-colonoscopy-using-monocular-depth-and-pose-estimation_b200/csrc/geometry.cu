@@ -13,77 +13,110 @@
 namespace dav2 {
 
 // ----------------------------------------------------------------------------------------------
-// back-projection: 4 pixels per thread, float4 load, 3x float4 + uchar4 streaming stores
+// back-projection: 8 pixels per thread (two float4 loads issued up front), 6x float4 + 2x uchar4 streaming
+// stores.  fp64 math in registers; the fp64<->fp32 / int->fp64 conversions run on the XU pipe (16/clk/SM),
+// which is what bounded the first version (ncu: XU 62 %, 34 % occupancy, 3.8 TB/s) -- so the pixel
+// coordinates are converted once per float4 and advanced by fp64 adds, and (row, col) comes from a
+// multiply-high instead of an integer division (another three XU ops).
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool backproject_one(float d, int u, int v, double fx_inv, double fy_inv, double cx,
-                                                double cy, const double (&T)[12], bool hasT, double inv_scale, double trunc,
-                                                float& X, float& Y, float& Z) {
-  double z = (double)d * inv_scale;
-  const bool ok = (z > 0.0) && (z < trunc) && isfinite(d);  // NaN fails z > 0
-  if (!ok) {
-    X = Y = Z = 0.f;
-    return false;
-  }
-  double x = ((double)u - cx) * fx_inv * z;
-  double y = ((double)v - cy) * fy_inv * z;
-  if (hasT) {
-    const double xw = T[0] * x + T[1] * y + T[2] * z + T[3];
-    const double yw = T[4] * x + T[5] * y + T[6] * z + T[7];
-    const double zw = T[8] * x + T[9] * y + T[10] * z + T[11];
+struct BpFrame {
+  double fx_inv, fy_inv, cx, cy, inv_scale, trunc;
+  double T[12];
+  bool hasT;
+};
+
+__device__ __forceinline__ bool backproject_one(float d, double xf, double yf, const BpFrame& f, float& X, float& Y, float& Z) {
+  double z = (double)d * f.inv_scale;
+  const bool ok = (z > 0.0) && (z < f.trunc) && isfinite(d);  // NaN fails z > 0
+  double x = xf * z;
+  double y = yf * z;
+  if (f.hasT) {
+    const double xw = f.T[0] * x + f.T[1] * y + f.T[2] * z + f.T[3];
+    const double yw = f.T[4] * x + f.T[5] * y + f.T[6] * z + f.T[7];
+    const double zw = f.T[8] * x + f.T[9] * y + f.T[10] * z + f.T[11];
     x = xw; y = yw; z = zw;
   }
-  X = (float)x; Y = (float)y; Z = (float)z;
-  return true;
+  X = ok ? (float)x : 0.f; Y = ok ? (float)y : 0.f; Z = ok ? (float)z : 0.f;
+  return ok;
+}
+
+// 4 consecutive pixels starting at linear index p0 (row-major); returns the number of valid ones
+__device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, int W, unsigned wmagic, const BpFrame& f,
+                                                float (&o)[12], uchar4& m) {
+  // v = p0 / W: multiply-high by ceil(2^32 / W) is exact while p0 * W < 2^32 (checked by the launcher)
+  const unsigned v = wmagic ? __umulhi(p0, wmagic) : p0 / (unsigned)W;
+  int u = (int)(p0 - v * (unsigned)W);
+  double ud = (double)u, vd = (double)v;
+  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+  uint8_t* mm = &m.x;
+  int nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then one multiply differs by <= 1 ulp(fp64)
+    const double xf = (ud - f.cx) * f.fx_inv, yf = (vd - f.cy) * f.fy_inv;
+    const bool ok = backproject_one(dd[k], xf, yf, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
+    mm[k] = ok ? 1 : 0;
+    nvalid += ok ? 1 : 0;
+    const bool wrap = (++u == W);
+    u = wrap ? 0 : u;
+    ud = wrap ? 0.0 : ud + 1.0;
+    vd = wrap ? vd + 1.0 : vd;
+  }
+  return nvalid;
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(256) backproject_kernel(const float* __restrict__ depth, int H, int W,
-                                                          const double* __restrict__ K4, int k_per_frame,
-                                                          const double* __restrict__ T12, double inv_scale,
-                                                          double trunc, float* __restrict__ xyz,
-                                                          uint8_t* __restrict__ valid, int* __restrict__ counts) {
+__global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __restrict__ depth, int H, int W, unsigned wmagic,
+                                                             const double* __restrict__ K4, int k_per_frame,
+                                                             const double* __restrict__ T12, double inv_scale,
+                                                             double trunc, float* __restrict__ xyz,
+                                                             uint8_t* __restrict__ valid, int* __restrict__ counts) {
   const int b = blockIdx.y;
   const long long HW = (long long)H * W;
   const double* K = K4 + (k_per_frame ? 4 * b : 0);
-  // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then one multiply differs by <= 1 ulp(fp64)
-  const double fx_inv = 1.0 / K[0], fy_inv = 1.0 / K[1], cx = K[2], cy = K[3];
-  double T[12];
-  const bool hasT = T12 != nullptr;
+  BpFrame f;
+  f.fx_inv = 1.0 / K[0]; f.fy_inv = 1.0 / K[1]; f.cx = K[2]; f.cy = K[3];
+  f.inv_scale = inv_scale; f.trunc = trunc;
+  f.hasT = T12 != nullptr;
 #pragma unroll
-  for (int i = 0; i < 12; ++i) T[i] = hasT ? T12[12 * b + i] : 0.0;
+  for (int i = 0; i < 12; ++i) f.T[i] = f.hasT ? T12[12 * b + i] : 0.0;
   const float* dfrm = depth + b * HW;
   float* ofrm = xyz + b * HW * 3;
   uint8_t* vfrm = valid ? valid + b * HW : nullptr;
   int nvalid = 0;
   if (VEC4) {
-    const long long nvec = HW >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-      const float4 d4 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i);
-      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const unsigned nvec = (unsigned)(HW >> 2);
+    // a block owns 512 consecutive float4s; thread t takes t and t + 256 (both loads in flight before any math)
+    for (unsigned base = blockIdx.x * 512u; base < nvec; base += gridDim.x * 512u) {
+      const unsigned i0 = base + threadIdx.x, i1 = i0 + 256u;
+      const bool h0 = i0 < nvec, h1 = i1 < nvec;
+      float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+      if (h0) d0 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i0);
+      if (h1) d1 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i1);
       float o[12];
       uchar4 m;
-      uint8_t* mm = &m.x;
-      const long long p0 = i * 4;
-      int v = (int)(p0 / W);
-      int u = (int)(p0 - (long long)v * W);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool ok = backproject_one(dd[k], u, v, fx_inv, fy_inv, cx, cy, T, hasT, inv_scale, trunc, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
-        mm[k] = ok ? 1 : 0;
-        nvalid += ok ? 1 : 0;
-        if (++u == W) { u = 0; ++v; }
+      if (h0) {
+        nvalid += backproject_quad(d0, i0 * 4u, W, wmagic, f, o, m);
+        float4* op = reinterpret_cast<float4*>(ofrm) + 3ll * i0;
+        __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
+        __stcs(op + 1, make_float4(o[4], o[5], o[6], o[7]));
+        __stcs(op + 2, make_float4(o[8], o[9], o[10], o[11]));
+        if (vfrm) __stcs(reinterpret_cast<uchar4*>(vfrm) + i0, m);
       }
-      float4* op = reinterpret_cast<float4*>(ofrm) + 3 * i;
-      __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
-      __stcs(op + 1, make_float4(o[4], o[5], o[6], o[7]));
-      __stcs(op + 2, make_float4(o[8], o[9], o[10], o[11]));
-      if (vfrm) __stcs(reinterpret_cast<uchar4*>(vfrm) + i, m);
+      if (h1) {
+        nvalid += backproject_quad(d1, i1 * 4u, W, wmagic, f, o, m);
+        float4* op = reinterpret_cast<float4*>(ofrm) + 3ll * i1;
+        __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
+        __stcs(op + 1, make_float4(o[4], o[5], o[6], o[7]));
+        __stcs(op + 2, make_float4(o[8], o[9], o[10], o[11]));
+        if (vfrm) __stcs(reinterpret_cast<uchar4*>(vfrm) + i1, m);
+      }
     }
   } else {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
       const int v = (int)(i / W), u = (int)(i - (long long)v * W);
       float X, Y, Z;
-      const bool ok = backproject_one(dfrm[i], u, v, fx_inv, fy_inv, cx, cy, T, hasT, inv_scale, trunc, X, Y, Z);
+      const bool ok = backproject_one(dfrm[i], ((double)u - f.cx) * f.fx_inv, ((double)v - f.cy) * f.fy_inv, f, X, Y, Z);
       ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
       if (vfrm) vfrm[i] = ok ? 1 : 0;
       nvalid += ok ? 1 : 0;
@@ -110,22 +143,24 @@ int launch_backproject(const float* depth, int B, int H, int W, const double* K4
   DAV2_CHECK(depth_scale > 0.f, "backproject: depth_scale must be > 0");
   if (counts) DAV2_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * B, stream));
   const long long HW = (long long)H * W;
+  DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
   const double inv_scale = 1.0 / (double)depth_scale;
   const double trunc = (double)depth_trunc;  // +inf disables truncation
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(valid) & 3) == 0);
-  const long long work = vec ? HW / 4 : HW;
-  long long bx = (work + 255) / 256;
-  // keep (bx * B) a few waves of the 148 SMs x 8 resident CTAs; grid-stride covers the rest
-  const long long cap = ((long long)sm_count() * 8 * 4 + B - 1) / B;
+  // multiply-high division by W is exact for p < 2^32 / W  (p < HW); otherwise the kernel divides
+  const unsigned wmagic = (W > 1 && HW * (long long)W < (1ll << 32)) ? (unsigned)((1ull << 32) / (unsigned)W + 1ull) : 0u;
+  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
+  // (bx * B) beyond ~16 waves of the 148 SMs x 3 resident CTAs buys nothing; the block-stride loop covers the rest
+  const long long cap = ((long long)sm_count() * 3 * 16 + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (valid ? 17.0 : 16.0), stream);
   dim3 grid((unsigned)bx, (unsigned)B);
   if (vec)
-    backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
+    backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
   else
-    backproject_kernel<false><<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
+    backproject_kernel<false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
   DAV2_LAUNCH_OK();
   return 0;
 }
@@ -134,45 +169,66 @@ int launch_backproject(const float* depth, int B, int H, int W, const double* K4
 // depth metrics: partial sums {n, S|d|, S|d|/(gt+1e-6), Sd^2, Sgt, #(t<a), #(t<b), #(t<c)}, t = max(gt/pred, pred/gt)
 //   variant 0 (compute_errors / test_step): valid = lo <= gt <= hi ; thresholds 1.1 (b, c unused = 1.1)
 //   variant 1 (calculate_metrics):          valid = gt>0 & pred>0 & !isinf(gt) & !isinf(pred); 1.25, 1.25^2, 1.25^3
+//   variants 2 / 3: variants 0 / 1 without a mask (every element counts)
 // ----------------------------------------------------------------------------------------------
+// Element-wise values are fp32 exactly as the reference computes them (torch / numpy fp32 ops, IEEE division);
+// they are summed in fp32 over 8 pixels and then folded into fp64 accumulators.  (Converting every term to fp64
+// put 4 F2F + 3 RCP per pixel on the XU pipe: ncu showed XU 94 % and 2.3 TB/s for the first version.)
+struct MetricAccF {
+  float s_abs, s_rel, s_sq, s_gt;
+  unsigned int n, na, nb, nc;
+};
 struct MetricAcc {
   double s_abs, s_rel, s_sq, s_gt;
   unsigned int n, na, nb, nc;
 };
 
 template <int VARIANT>
-__device__ __forceinline__ void metric_accum(MetricAcc& a, float p, float g, float lo, float hi) {
+__device__ __forceinline__ void metric_accum(MetricAccF& a, float p, float g, float lo, float hi) {
   bool ok;
   if (VARIANT == 0)
     ok = (g >= lo) && (g <= hi);
   else if (VARIANT == 1)
     ok = (g > 0.f) && (p > 0.f) && !isinf(g) && !isinf(p);
   else
-    ok = true;  // variant 2: inputs were masked by the caller (plain compute_errors)
-  if (!ok) return;
+    ok = true;  // variants 2 / 3: every element counts (plain compute_errors / calculate_metrics(mask_invalid=False))
+  constexpr bool CM = (VARIANT == 1 || VARIANT == 3);  // calculate_metrics definitions
   const float d = p - g;
   const float ad = fabsf(d);
-  a.s_abs += (double)ad;
-  a.s_rel += (double)(ad / (g + 1e-6f));
-  a.s_sq += (double)(d * d);
-  a.s_gt += (double)g;
-  a.n += 1;
   const float t = fmaxf(g / p, p / g);
-  if (VARIANT != 1) {
-    a.na += (t < 1.1f) ? 1 : 0;
-    a.nb += isnan(p) ? 1 : 0;  // eval/evaluation.py:33-36 NaN / Inf warnings
-    a.nc += isinf(p) ? 1 : 0;
+  a.s_abs += ok ? ad : 0.f;
+  if (!CM) a.s_rel += ok ? ad / (g + 1e-6f) : 0.f;  // calculate_metrics divides the means instead
+  a.s_sq += ok ? d * d : 0.f;
+  a.s_gt += ok ? g : 0.f;
+  a.n += ok ? 1 : 0;
+  if (!CM) {
+    a.na += (ok && t < 1.1f) ? 1 : 0;
+    a.nb += (ok && isnan(p)) ? 1 : 0;  // eval/evaluation.py:33-36 NaN / Inf warnings
+    a.nc += (ok && isinf(p)) ? 1 : 0;
   } else {
-    a.na += (t < 1.25f) ? 1 : 0;
-    a.nb += (t < 1.5625f) ? 1 : 0;
-    a.nc += (t < 1.953125f) ? 1 : 0;
+    a.na += (ok && t < 1.25f) ? 1 : 0;
+    a.nb += (ok && t < 1.5625f) ? 1 : 0;
+    a.nc += (ok && t < 1.953125f) ? 1 : 0;
   }
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(256) depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                                            long long HW, float lo, float hi, int per_frame,
-                                                            double* __restrict__ partials) {
+__device__ __forceinline__ void metric_quad(MetricAccF& a, const float4& p4, const float4& g4, float lo, float hi) {
+  metric_accum<VARIANT>(a, p4.x, g4.x, lo, hi);
+  metric_accum<VARIANT>(a, p4.y, g4.y, lo, hi);
+  metric_accum<VARIANT>(a, p4.z, g4.z, lo, hi);
+  metric_accum<VARIANT>(a, p4.w, g4.w, lo, hi);
+}
+
+__device__ __forceinline__ void metric_fold(MetricAcc& a, const MetricAccF& c) {
+  a.s_abs += (double)c.s_abs; a.s_rel += (double)c.s_rel; a.s_sq += (double)c.s_sq; a.s_gt += (double)c.s_gt;
+  a.n += c.n; a.na += c.na; a.nb += c.nb; a.nc += c.nc;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 4) depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                               long long HW, float lo, float hi, int per_frame,
+                                                               double* __restrict__ partials) {
   const int b = blockIdx.y;
   const float* pf = pred + b * HW;
   const float* gf = gt + b * HW;
@@ -180,17 +236,25 @@ __global__ void __launch_bounds__(256) depth_metrics_kernel(const float* __restr
   const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(gt)) & 15) == 0);
   if (vec) {
     const long long nvec = HW >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-      const float4 p4 = __ldcs(reinterpret_cast<const float4*>(pf) + i);
-      const float4 g4 = __ldcs(reinterpret_cast<const float4*>(gf) + i);
-      metric_accum<VARIANT>(a, p4.x, g4.x, lo, hi);
-      metric_accum<VARIANT>(a, p4.y, g4.y, lo, hi);
-      metric_accum<VARIANT>(a, p4.z, g4.z, lo, hi);
-      metric_accum<VARIANT>(a, p4.w, g4.w, lo, hi);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // a block owns 512 consecutive float4 pairs per trip; four 16-byte loads are in flight per thread
+    for (long long base = (long long)blockIdx.x * 512; base < nvec; base += (long long)gridDim.x * 512) {
+      const long long i0 = base + threadIdx.x, i1 = i0 + 256;
+      const bool h0 = i0 < nvec, h1 = i1 < nvec;
+      float4 p0 = zero, g0 = zero, p1 = zero, g1 = zero;
+      if (h0) { p0 = __ldcs(reinterpret_cast<const float4*>(pf) + i0); g0 = __ldcs(reinterpret_cast<const float4*>(gf) + i0); }
+      if (h1) { p1 = __ldcs(reinterpret_cast<const float4*>(pf) + i1); g1 = __ldcs(reinterpret_cast<const float4*>(gf) + i1); }
+      MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
+      if (h0) metric_quad<VARIANT>(c, p0, g0, lo, hi);
+      if (h1) metric_quad<VARIANT>(c, p1, g1, lo, hi);
+      metric_fold(a, c);
     }
   } else {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
-      metric_accum<VARIANT>(a, pf[i], gf[i], lo, hi);
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < HW; i0 += (long long)gridDim.x * blockDim.x * 8) {
+      MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
+      for (long long i = i0; i < i0 + 8 && i < HW; ++i) metric_accum<VARIANT>(c, pf[i], gf[i], lo, hi);
+      metric_fold(a, c);
+    }
   }
   double v[8] = {(double)a.n, a.s_abs, a.s_rel, a.s_sq, a.s_gt, (double)a.na, (double)a.nb, (double)a.nc};
 #pragma unroll
@@ -217,10 +281,12 @@ int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW
     return 0;
   }
   DAV2_CHECK(pred && gt, "depth_metrics: null pointer");
-  DAV2_CHECK(variant >= 0 && variant <= 2, "depth_metrics: variant must be 0 (test_step mask), 1 (calculate_metrics) or 2 (no mask)");
+  DAV2_CHECK(variant >= 0 && variant <= 3,
+             "depth_metrics: variant must be 0 (test_step mask), 1 (calculate_metrics), 2 (compute_errors, no mask) or 3 "
+             "(calculate_metrics, no mask)");
   DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
-  long long bx = (HW / 4 + 255) / 256;
-  const long long cap = ((long long)sm_count() * 8 * 2 + B - 1) / B;
+  long long bx = (HW / 4 + 511) / 512;
+  const long long cap = ((long long)sm_count() * 4 * 8 + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   ProfScope ps(PC_METRICS, 0.0, (double)B * HW * 8.0, stream);
@@ -229,8 +295,10 @@ int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW
     depth_metrics_kernel<0><<<grid, 256, 0, stream>>>(pred, gt, HW, lo, hi, per_frame, partials);
   else if (variant == 1)
     depth_metrics_kernel<1><<<grid, 256, 0, stream>>>(pred, gt, HW, lo, hi, per_frame, partials);
-  else
+  else if (variant == 2)
     depth_metrics_kernel<2><<<grid, 256, 0, stream>>>(pred, gt, HW, lo, hi, per_frame, partials);
+  else
+    depth_metrics_kernel<3><<<grid, 256, 0, stream>>>(pred, gt, HW, lo, hi, per_frame, partials);
   DAV2_LAUNCH_OK();
   return 0;
 }

@@ -116,7 +116,7 @@ static inline int vgrid(long long n) {
 
 int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, long long n, double voxel, float* out_xyz,
                             float* out_rgb, long long* out_count, cudaStream_t stream) {
-  DAV2_CHECK(xyz && out_xyz && out_count && n >= 0 && voxel > 0.0, "voxel_downsample: bad arguments");
+  DAV2_CHECK(out_count && n >= 0 && voxel > 0.0 && (n == 0 || (xyz && out_xyz)), "voxel_downsample: bad arguments");
   DAV2_CHECK(n < (1ll << 31), "voxel_downsample: at most 2^31-1 points per call");
   DAV2_CHECK(!out_rgb || rgb, "voxel_downsample: out_rgb without rgb");
   if (n == 0) {

@@ -109,9 +109,10 @@ int dav2_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* val
  *              (eval/evaluation.py:16-60, lightning_model.py:304-313)
  *   variant 1: calculate_metrics.calculate_metrics mask gt>0 & pred>0 & finite (calculate_metrics.py:17-55)
  *   variant 2: evaluation.compute_errors on inputs the caller already masked (every element counts)
+ *   variant 3: calculate_metrics(mask_invalid=False) (every element counts)
  *   partials   device fp64 [B,8] (per_frame=1) or [8]:
  *              {n, sum|d|, sum|d|/(gt+1e-6), sum d^2, sum gt, #(t<a), #(t<b), #(t<c)}, t = max(gt/pred, pred/gt),
- *              (a,b,c) = (1.25, 1.25^2, 1.25^3) for variant 1; for variants 0 and 2 slot 5 is #(t<1.1) and
+ *              (a,b,c) = (1.25, 1.25^2, 1.25^3) for variants 1 and 3; for variants 0 and 2 slot 5 is #(t<1.1) and
  *              slots 6, 7 count NaN / Inf predictions (the warnings of eval/evaluation.py:33-36). */
 int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float lo, float hi,
                        int32_t variant, int32_t per_frame, double* partials, void* stream);

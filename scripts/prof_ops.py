@@ -40,5 +40,26 @@ if what in ("attn", "all"):
     qkv = rnd(M, 3 * D)
     for _ in range(reps):
         ops.attention_h16(qkv, 64, 1370, D)
+if what in ("geom",):
+    B, H, W = 64, 518, 518
+    depth = torch.rand(B, H, W, generator=g, device=dev) * 20.0
+    gt = torch.rand(B, H, W, generator=g, device=dev)
+    T12 = torch.eye(4, dtype=torch.float64)[:3].reshape(1, 12).repeat(B, 1) + 0.01
+    for _ in range(reps):
+        xyz, valid, counts = ops.backproject(depth, (170.1677, 169.8526, 194.7248, 198.2624), T12)
+        ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False)
+        ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 1, True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    for name, fn in (("backproject", lambda: ops.backproject(depth, (170.1677, 169.8526, 194.7248, 198.2624), T12, out_xyz=xyz)),
+                     ("metrics0", lambda: ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False))):
+        fn(); torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(20): fn()
+        ev[1].record(); torch.cuda.synchronize()
+        print(name, "us/launch (warm, back to back)", ev[0].elapsed_time(ev[1]) / 20 * 1e3)
+    pts = xyz[:8].reshape(-1, 3)
+    ev[0].record(); q, _ = ops.voxel_downsample(pts, 0.01, valid=valid[:8].reshape(-1)); ev[1].record(); torch.cuda.synchronize()
+    print("voxel 8 frames", pts.shape[0], "->", q.shape[0], "ms", ev[0].elapsed_time(ev[1]))
 torch.cuda.synchronize()
 print("ok")

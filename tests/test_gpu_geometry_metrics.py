@@ -266,3 +266,15 @@ def test_voxel_downsample_edges_and_api():
     np.testing.assert_allclose(ds.points, ref, atol=1e-7)
     np.testing.assert_allclose(ds.colors, refc, atol=2e-7)
     assert len(d2p.PointCloud().voxel_down_sample(0.01)) == 0
+
+
+def test_calculate_metrics_unmasked_variant():
+    """calculate_metrics(gt, pred, mask_invalid=False) (calculate_metrics.py:17-21 skipped): every pixel counts."""
+    from dav2_b200 import calculate_metrics as cm
+    rng = np.random.default_rng(11)
+    gt = rng.gamma(2.0, 0.05, (70, 98)).astype(np.float32) + 1e-3
+    pred = (gt * rng.normal(1.0, 0.2, gt.shape)).astype(np.float32).clip(1e-3)
+    got = cm.calculate_metrics(gt, pred, mask_invalid=False)
+    ref = met.calculate_metrics(gt, pred, mask_invalid=False)
+    for k in CM_KEYS:
+        assert abs(got[k] - ref[k]) <= METRIC_TOL * max(1.0, abs(ref[k])), k
