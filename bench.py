@@ -175,7 +175,10 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="tensor-core operand format (fp16 = the reference's AMP 16-mixed; fp32 accumulate either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL cloud gather (N>1)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the cloud gather (N>1)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = the back-projection kernel stores into every rank's peer-mapped gather buffer "
+                         "(sharding.CloudGather); 'nccl' = local back-projection + all_gather_into_tensor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -183,7 +186,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from dav2_b200 import _lib, evaluation, ops, weights
+    from dav2_b200 import _lib, evaluation, ops, sharding, weights
     from dav2_b200.dpt import MODEL_CONFIGS, DepthAnythingV2
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,15 +213,23 @@ def main():
     rel = synth_rel_poses(B, dev, 5 + rank)
     k4 = torch.tensor(K518, dtype=torch.float64, device=dev)
     xyz = torch.empty(B, HW, 3, dtype=torch.float32, device=dev)
-    cloud_all = mask_all = None
+    cloud_all = mask_all = fused = None
     if world > 1 and not args.no_gather:
-        cloud_all = torch.empty(world, B, HW, 3, dtype=torch.float32, device=dev)
-        mask_all = torch.empty(world, B, HW, dtype=torch.uint8, device=dev)
+        if args.gather == "fused":
+            fused = sharding.CloudGather(B, HW, dev)  # peer-mapped gather buffers (CUDA IPC over NVLink), double buffered
+        else:
+            cloud_all = torch.empty(world, B, HW, 3, dtype=torch.float32, device=dev)
+            mask_all = torch.empty(world, B, HW, dtype=torch.uint8, device=dev)
 
     def step(x, gt):
         depth = model(x)
         _, T12 = ops.compose_poses(rel, None, want_T12=True)
-        _, valid, counts = ops.backproject(depth, k4, T12[1:], out_xyz=xyz)
+        if fused is not None:
+            # the kernel's stores ARE the all-gather; the metric all-reduce below orders readers after all writers
+            _, _, counts_all = fused.backproject(depth, k4, T12[1:])
+            counts = counts_all[rank * B:(rank + 1) * B]
+        else:
+            _, valid, counts = ops.backproject(depth, k4, T12[1:], out_xyz=xyz)
         part = evaluation.metric_partials(depth[:, None], gt, 1e-6, 20.0)
         if world > 1:
             dist.all_reduce(part)  # partial SUMS, finalised after the reduce
@@ -312,6 +323,8 @@ def main():
     h2d = B * 3 * HW * 4 + B * HW * 4
     d2h = 8 * 8 + 4 * B
 
+    if fused is not None:
+        fused.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -339,7 +352,9 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"BASELINE configs[2]: DepthAnythingV2 {args.encoder} batch {B}/GPU, {S}x{S} synthetic SimCol-shaped "
                                "frames, random-init weights; depth + pose chain + fused back-projection/SE(3)/validity + metric "
-                               "partial sums" + ("; NCCL all-reduce of sums + all-gather of clouds" if world > 1 else ""),
+                               "partial sums" + (("; NCCL all-reduce of sums; clouds gathered by the back-projection kernel's stores into "
+                                                   "peer-mapped buffers" if fused is not None else
+                                                   "; NCCL all-reduce of sums + all-gather of clouds") if world > 1 else ""),
                    "encoder": args.encoder, "batch_per_gpu": B, "size": S,
                    "l2": f"inputs re-read every step are {B * 3 * HW * 4 / 1e6:.0f} MB and activations >10 GB, larger than the 126 MB L2"},
         "clocks": clocks,

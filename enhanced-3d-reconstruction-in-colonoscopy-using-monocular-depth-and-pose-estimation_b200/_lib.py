@@ -39,6 +39,13 @@ SIGNATURES = {
     "dav2_preprocess_bgr_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dav2_backproject": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dav2_backproject_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
+                                        C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_i64, c_void_p]),
+    "dav2_peer_alloc": (c_int, [C.POINTER(c_void_p), c_i64]),
+    "dav2_peer_free": (c_int, [c_void_p]),
+    "dav2_peer_export": (c_int, [c_void_p, c_void_p]),
+    "dav2_peer_open": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "dav2_peer_close": (c_int, [c_void_p]),
     "dav2_voxel_downsample": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, C.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_depth_metrics": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
     "dav2_compose_poses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -1,4 +1,5 @@
 // extern "C" surface of libdav2_b200.so (declared in include/dav2_b200.h).
+#include <string.h>
 #include <new>
 
 #include "posenet.cuh"
@@ -97,6 +98,58 @@ int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const 
                      int32_t* counts, void* stream) {
   if (int rc = require_sm100()) return rc;
   return launch_backproject(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, xyz, valid, counts, S(stream));
+}
+
+int dav2_backproject_gather(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
+                            const double* T12, float depth_scale, float depth_trunc, float* const* xyz_dst,
+                            uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset,
+                            void* stream) {
+  if (int rc = require_sm100()) return rc;
+  if (!xyz_dst || n_dst < 1 || n_dst > 8 || frame_offset < 0 || H <= 0 || W <= 0) {
+    dav2::set_last_error("backproject_gather: bad destination list");
+    return -2;
+  }
+  const long long HW = (long long)H * W;
+  float* x[8];
+  uint8_t* v[8];
+  int* c[8];
+  for (int p = 0; p < n_dst; ++p) {
+    x[p] = xyz_dst[p] ? xyz_dst[p] + frame_offset * HW * 3 : nullptr;
+    v[p] = (valid_dst && valid_dst[p]) ? valid_dst[p] + frame_offset * HW : nullptr;
+    c[p] = (counts_dst && counts_dst[p]) ? counts_dst[p] + frame_offset : nullptr;
+  }
+  return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, x, valid_dst ? v : nullptr,
+                                  counts_dst ? c : nullptr, n_dst, S(stream));
+}
+
+// ---- peer-mapped buffers (CUDA IPC) for the fused gather ----
+int dav2_peer_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) { dav2::set_last_error("peer_alloc: bad arguments"); return -2; }
+  DAV2_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
+  return 0;
+}
+int dav2_peer_free(void* ptr) {
+  DAV2_CUDA_OK(cudaFree(ptr));
+  return 0;
+}
+int dav2_peer_export(const void* ptr, uint8_t* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle64) { dav2::set_last_error("peer_export: null pointer"); return -2; }
+  cudaIpcMemHandle_t h;
+  DAV2_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int dav2_peer_open(const uint8_t* handle64, void** ptr) {
+  if (!ptr || !handle64) { dav2::set_last_error("peer_open: null pointer"); return -2; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DAV2_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int dav2_peer_close(void* ptr) {
+  DAV2_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return 0;
 }
 
 int dav2_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, int64_t n, double voxel_size, float* out_xyz,

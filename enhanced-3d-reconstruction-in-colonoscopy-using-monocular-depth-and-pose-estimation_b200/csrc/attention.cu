@@ -1,16 +1,24 @@
 // Fused flash-style attention for DINOv2 (d_head = 64, non-causal, arbitrary token count) on sm_100a.
 //
 // One CTA = one 128-query tile of one (image, head); 2 CTAs co-reside per SM so that one CTA's
-// softmax (MUFU-bound) overlaps the other's tensor-core work.
-//   warp 0 (1 lane) : TMA producer  - Q once, then K/V tiles through a 2-deep smem ring
-//   warp 1 (1 lane) : MMA issuer    - S = Q K^T (tcgen05, 128x128x64 -> TMEM cols [0,128)),
+// softmax overlaps the other's tensor-core work.  256 threads = two warpgroups:
+//   WG0 warp 0      : TMA producer  - Q once, then K/V tiles through a 2-deep smem ring
+//   WG0 warp 1      : MMA issuer    - S = Q K^T (tcgen05, 128x128x64 -> TMEM cols [0,128)),
 //                                     O += P V (128x64x128 -> TMEM cols [128,192)), V is the
 //                                     MN-major B operand straight from the [token, 3D] qkv buffer
-//   warps 2..5      : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
+//   WG0 warps 2,3   : idle (they only exist so that setmaxnreg can hand WG0's registers to WG1)
+//   WG1 warps 4..7  : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
 //                                     fp32, P -> h16 into 128B-swizzled smem (A operand of the PV MMA),
-//                                     running O kept in registers (o = o*alpha + O_part)
+//                                     O accumulates in TMEM (lazy rescale)
+// Softmax arithmetic (the bound of this kernel: 16 MUFU/clk/SM = 1024 cycles per 128x128 tile against 512
+// tensor-pipe cycles): packed fp32 (FFMA2/FADD2) for the scale-subtract and the row sums, and EMU of every 8
+// element pairs take their 2^x from a Cody-Waite + degree-3 polynomial on the FMA pipe instead of MUFU.EX2
+// (max rel. error 7.5e-5, below the 4.9e-4 rounding of P to fp16), which balances the XU pipe against issue slots.
+// WG1 runs with 208 registers (setmaxnreg) so the 128-wide S row plus the exp pipeline stay in registers with ILP.
 // Q was pre-scaled by d^-1/2 = 0.125 (folded exactly into the qkv weights), so S needs no scale.
 // Reads qkv h16 [B*N, 3*D] (q | k | v, head h at columns h*64), writes out h16 [B*N, D].
+#include <stdlib.h>
+
 #include "gemm_epilogue.cuh"
 
 namespace dav2 {
@@ -34,14 +42,41 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for a pair, on the FMA/ALU pipes: n = round(x) by the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5],
+// p(f) ~ 2^f (degree-3 minimax, rel. err 7.5e-5), result = p with n added to its exponent field.
+// SASS: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair.
+__device__ __forceinline__ float2 ex2_emu2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 r = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(r, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.05517118f, 0.05517118f), f, make_float2(0.24260994f, 0.24260994f));
+  p = __ffma2_rn(p, f, make_float2(0.69326096f, 0.69326096f));
+  p = __ffma2_rn(p, f, make_float2(0.99992815f, 0.99992815f));
+  float2 o;
+  o.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
+  o.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return o;
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
   return r;
 }
 
-template <bool FP16>
-__global__ void __launch_bounds__(192, 2)
+template <bool FP16, int EMU>
+__global__ void __launch_bounds__(256, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
@@ -81,6 +116,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
+  if (warp < 4) {
+  setmaxnreg_dec<48>();
   if (warp == 0) {
     // ---------------- TMA producer (whole warp, elected lane issues) ----------------
     if (elect_one()) {
@@ -142,7 +179,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       }
       __syncwarp();
     }
-  } else if (warp >= 2) {
+  }
+  } else {
+    setmaxnreg_inc<208>();
     // ---------------- softmax / output (one query row per thread) ----------------
     // The whole S row (128 fp32) is pulled into registers with ONE exposed TMEM round trip, which frees the
     // S buffer at once (the issuer overlaps S(j+1) with this tile's softmax).  O accumulates in TMEM across
@@ -209,19 +248,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         }
       }
       const float mscaled = m_ref * LOG2E;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      const float2 l2e2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mscaled, -mscaled);
+      float2 rs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t preg[64];
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        const float e0 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i]), LOG2E, -mscaled));
-        const float e1 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 1]), LOG2E, -mscaled));
-        const float e2 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 2]), LOG2E, -mscaled));
-        const float e3 = fast_exp2(fmaf(__uint_as_float(sreg[2 * i + 3]), LOG2E, -mscaled));
-        rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
-        // in place: slots i, i+1 <= 2i are already consumed
-        sreg[i] = FP16 ? pack2<FMT_F16>(e0, e1) : pack2<FMT_BF16>(e0, e1);
-        sreg[i + 1] = FP16 ? pack2<FMT_F16>(e2, e3) : pack2<FMT_BF16>(e2, e3);
+      for (int i = 0; i < 64; ++i) {  // pair i = keys 2i, 2i+1
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[2 * i]), __uint_as_float(sreg[2 * i + 1])), l2e2, nm2);
+        float2 e;
+        if ((i & 7) < EMU) {
+          e = ex2_emu2(x);
+        } else {
+          e.x = fast_exp2(x.x);
+          e.y = fast_exp2(x.y);
+        }
+        rs[i & 3] = __fadd2_rn(rs[i & 3], e);
+        preg[i] = FP16 ? pack2<FMT_F16>(e.x, e.y) : pack2<FMT_BF16>(e.x, e.y);
       }
-      l += (rs0 + rs1) + (rs2 + rs3);
+      l += ((rs[0].x + rs[0].y) + (rs[1].x + rs[1].y)) + ((rs[2].x + rs[2].y) + (rs[3].x + rs[3].y));
       if (j > 0 && !o_waited) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P buffer
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -229,8 +272,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t chunk = (uint32_t)((c & 1) * 4 + g) ^ ((uint32_t)r & 7u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(sreg[c * 16 + 4 * g]),
-                       "r"(sreg[c * 16 + 4 * g + 1]), "r"(sreg[c * 16 + 4 * g + 2]), "r"(sreg[c * 16 + 4 * g + 3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(preg[c * 16 + 4 * g]),
+                       "r"(preg[c * 16 + 4 * g + 1]), "r"(preg[c * 16 + 4 * g + 2]), "r"(preg[c * 16 + 4 * g + 3])
                        : "memory");
         }
       }
@@ -278,11 +321,17 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   DAV2_CHECK(D % 64 == 0 && N > 0 && B > 0, "attention: bad shape B=%d N=%d D=%d", B, N, D);
   CUtensorMap tm;
   if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;
-  static bool configured = false;
-  if (!configured) {
-    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
+  // pairs out of every 8 whose 2^x is emulated on the FMA pipe (tuned on B200; DAV2_ATTN_EMU overrides for profiling)
+  static int emu = -1;
+  if (emu < 0) {
+    const char* e = getenv("DAV2_ATTN_EMU");
+    emu = e ? atoi(e) : 2;
+    DAV2_CHECK(emu == 0 || emu == 2 || emu == 3 || emu == 4, "DAV2_ATTN_EMU must be 0, 2, 3 or 4");
+#define DAV2_ATTN_CFG(F, E) \
+  DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM))
+    DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3); DAV2_ATTN_CFG(true, 4);
+    DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3); DAV2_ATTN_CFG(false, 4);
+#undef DAV2_ATTN_CFG
   }
   AttnParams p;
   p.out = out;
@@ -294,8 +343,18 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   p.fmt = fmt;
   dim3 grid((N + 127) / 128, D / 64, B);
   ProfScope ps(PC_ATTN, 4.0 * B * (D / 64) * (double)N * N * 64.0, 2.0 * 4.0 * B * (double)N * D, stream);
-  if (fmt == FMT_F16) attention_kernel<true><<<grid, 192, ATT_SMEM, stream>>>(tm, p);
-  else attention_kernel<false><<<grid, 192, ATT_SMEM, stream>>>(tm, p);
+#define DAV2_ATTN_GO(E)                                                                   \
+  do {                                                                                    \
+    if (fmt == FMT_F16) attention_kernel<true, E><<<grid, 256, ATT_SMEM, stream>>>(tm, p); \
+    else attention_kernel<false, E><<<grid, 256, ATT_SMEM, stream>>>(tm, p);               \
+  } while (0)
+  switch (emu) {
+    case 0: DAV2_ATTN_GO(0); break;
+    case 3: DAV2_ATTN_GO(3); break;
+    case 4: DAV2_ATTN_GO(4); break;
+    default: DAV2_ATTN_GO(2); break;
+  }
+#undef DAV2_ATTN_GO
   DAV2_LAUNCH_OK();
   return 0;
 }

@@ -19,24 +19,34 @@ namespace dav2 {
 // coordinates are converted once per float4 and advanced by fp64 adds, and (row, col) comes from a
 // multiply-high instead of an integer division (another three XU ops).
 // ----------------------------------------------------------------------------------------------
-struct BpFrame {
-  double fx_inv, fy_inv, cx, cy, inv_scale, trunc;
-  double T[12];
-  bool hasT;
+// Destinations of one launch: the local output, or -- for the fused back-projection + cloud all-gather -- the
+// gather buffer of EVERY rank (peer-mapped over NVLink; the store is the collective, SURVEY.md 8e phase 2).
+// All pointers are already offset to this rank's first frame.
+static constexpr int BP_MAX_DST = 8;
+struct BpDst {
+  float* xyz[BP_MAX_DST];
+  uint8_t* valid[BP_MAX_DST];
+  int* counts[BP_MAX_DST];
+  int n;
 };
 
-__device__ __forceinline__ bool backproject_one(float d, double xf, double yf, const BpFrame& f, float& X, float& Y, float& Z) {
-  double z = (double)d * f.inv_scale;
+// Per-frame constants.  X_w = R (z [xf, yf, 1]) + t = z * ray(u, v) + t with the world-frame ray
+// ray(u, v) = u*dx + v*dy + r0,  dx = R[:,0]/fx,  dy = R[:,1]/fy,  r0 = R[:,2] - cx*dx - cy*dy,
+// so a pixel costs 3 DFMA for its ray (ray_k = ray_0 + k*dx inside a quad) and 3 DFMA for the point instead of the
+// 20+ fp64 operations of the literal formula (the first versions were fp64-issue bound: 90 instructions / pixel,
+// 55 % issue at 33 % occupancy, 3.0 TB/s).  Differences to the oracle's operation order are ~1e-16 relative, far below
+// the single rounding to fp32 at the end.  Without a pose R = I, t = 0.
+struct BpFrame {
+  double dx[3], dy[3], r0[3], wrap[3], t[3];  // wrap = dy - W*dx: step from (u, v) to (u - W, v + 1)
+  double inv_scale, trunc;
+};
+
+__device__ __forceinline__ bool backproject_one(float d, const double (&ray)[3], const BpFrame& f, float& X, float& Y, float& Z) {
+  const double z = (double)d * f.inv_scale;
   const bool ok = (z > 0.0) && (z < f.trunc) && isfinite(d);  // NaN fails z > 0
-  double x = xf * z;
-  double y = yf * z;
-  if (f.hasT) {
-    const double xw = f.T[0] * x + f.T[1] * y + f.T[2] * z + f.T[3];
-    const double yw = f.T[4] * x + f.T[5] * y + f.T[6] * z + f.T[7];
-    const double zw = f.T[8] * x + f.T[9] * y + f.T[10] * z + f.T[11];
-    x = xw; y = yw; z = zw;
-  }
-  X = ok ? (float)x : 0.f; Y = ok ? (float)y : 0.f; Z = ok ? (float)z : 0.f;
+  X = ok ? (float)fma(z, ray[0], f.t[0]) : 0.f;
+  Y = ok ? (float)fma(z, ray[1], f.t[1]) : 0.f;
+  Z = ok ? (float)fma(z, ray[2], f.t[2]) : 0.f;
   return ok;
 }
 
@@ -45,22 +55,27 @@ __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, in
                                                 float (&o)[12], uchar4& m) {
   // v = p0 / W: multiply-high by ceil(2^32 / W) is exact while p0 * W < 2^32 (checked by the launcher)
   const unsigned v = wmagic ? __umulhi(p0, wmagic) : p0 / (unsigned)W;
-  int u = (int)(p0 - v * (unsigned)W);
-  double ud = (double)u, vd = (double)v;
+  const int u = (int)(p0 - v * (unsigned)W);
+  const int nrow = W - u;  // pixels k >= nrow of the quad are on row v + 1 (at most one row change: W >= 4)
+  const double ud = (double)u, vd = (double)(int)v;
+  double ra[3], rb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ra[c] = fma(ud, f.dx[c], fma(vd, f.dy[c], f.r0[c]));
+    rb[c] = ra[c] + f.wrap[c];
+  }
   const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
   uint8_t* mm = &m.x;
   int nvalid = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then one multiply differs by <= 1 ulp(fp64)
-    const double xf = (ud - f.cx) * f.fx_inv, yf = (vd - f.cy) * f.fy_inv;
-    const bool ok = backproject_one(dd[k], xf, yf, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
+    const bool same = k < nrow;
+    double ray[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ray[c] = fma((double)k, f.dx[c], same ? ra[c] : rb[c]);
+    const bool ok = backproject_one(dd[k], ray, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
     mm[k] = ok ? 1 : 0;
     nvalid += ok ? 1 : 0;
-    const bool wrap = (++u == W);
-    u = wrap ? 0 : u;
-    ud = wrap ? 0.0 : ud + 1.0;
-    vd = wrap ? vd + 1.0 : vd;
   }
   return nvalid;
 }
@@ -69,60 +84,99 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __restrict__ depth, int H, int W, unsigned wmagic,
                                                              const double* __restrict__ K4, int k_per_frame,
                                                              const double* __restrict__ T12, double inv_scale,
-                                                             double trunc, float* __restrict__ xyz,
-                                                             uint8_t* __restrict__ valid, int* __restrict__ counts) {
+                                                             double trunc, const BpDst dst) {
   const int b = blockIdx.y;
   const long long HW = (long long)H * W;
   const double* K = K4 + (k_per_frame ? 4 * b : 0);
-  BpFrame f;
-  f.fx_inv = 1.0 / K[0]; f.fy_inv = 1.0 / K[1]; f.cx = K[2]; f.cy = K[3];
-  f.inv_scale = inv_scale; f.trunc = trunc;
-  f.hasT = T12 != nullptr;
-#pragma unroll
-  for (int i = 0; i < 12; ++i) f.T[i] = f.hasT ? T12[12 * b + i] : 0.0;
+  // the frame constants (two fp64 divisions, ~150 instructions) are computed by three lanes and broadcast through
+  // shared memory; per thread that prologue cost a third of the 8-pixel body
+  __shared__ BpFrame fs;
+  if (threadIdx.x < 3) {
+    // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then multiplies differs by <= 1 ulp(fp64)
+    const int c = threadIdx.x;
+    const double fx_inv = 1.0 / K[0], fy_inv = 1.0 / K[1], cx = K[2], cy = K[3];
+    const bool hasT = T12 != nullptr;
+    const double r0c = hasT ? T12[12 * b + 4 * c] : (c == 0 ? 1.0 : 0.0), r1c = hasT ? T12[12 * b + 4 * c + 1] : (c == 1 ? 1.0 : 0.0),
+                 r2c = hasT ? T12[12 * b + 4 * c + 2] : (c == 2 ? 1.0 : 0.0);
+    fs.dx[c] = r0c * fx_inv;
+    fs.dy[c] = r1c * fy_inv;
+    fs.r0[c] = r2c - cx * (r0c * fx_inv) - cy * (r1c * fy_inv);
+    fs.wrap[c] = r1c * fy_inv - (double)W * (r0c * fx_inv);
+    fs.t[c] = hasT ? T12[12 * b + 4 * c + 3] : 0.0;
+    if (c == 0) {
+      fs.inv_scale = inv_scale;
+      fs.trunc = trunc;
+    }
+  }
   const float* dfrm = depth + b * HW;
-  float* ofrm = xyz + b * HW * 3;
-  uint8_t* vfrm = valid ? valid + b * HW : nullptr;
+  const long long ooff = b * HW * 3, voff = b * HW;
+  const bool has_valid = dst.valid[0] != nullptr;
   int nvalid = 0;
+  bool have_f = false;
+  BpFrame f;
   if (VEC4) {
     const unsigned nvec = (unsigned)(HW >> 2);
-    // a block owns 512 consecutive float4s; thread t takes t and t + 256 (both loads in flight before any math)
+    // Each thread's 4 points are 48 contiguous bytes; storing them directly makes every warp-wide store touch 12 lines
+    // with 16 of every 48 bytes (ncu: 1.94x the ideal number of L2 store sectors).  Stage the warp's 1536 bytes in
+    // shared memory (48-byte thread stride = conflict-free for 128-bit accesses) and write three fully coalesced
+    // 512-byte rows instead.
+    __shared__ float4 stage[8][96];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a block owns 512 consecutive float4s per trip; thread t takes t and t + 256 (both loads in flight before any math)
     for (unsigned base = blockIdx.x * 512u; base < nvec; base += gridDim.x * 512u) {
       const unsigned i0 = base + threadIdx.x, i1 = i0 + 256u;
       const bool h0 = i0 < nvec, h1 = i1 < nvec;
       float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
       if (h0) d0 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i0);
       if (h1) d1 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i1);
-      float o[12];
-      uchar4 m;
-      if (h0) {
-        nvalid += backproject_quad(d0, i0 * 4u, W, wmagic, f, o, m);
-        float4* op = reinterpret_cast<float4*>(ofrm) + 3ll * i0;
-        __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
-        __stcs(op + 1, make_float4(o[4], o[5], o[6], o[7]));
-        __stcs(op + 2, make_float4(o[8], o[9], o[10], o[11]));
-        if (vfrm) __stcs(reinterpret_cast<uchar4*>(vfrm) + i0, m);
+      if (!have_f) {  // block-uniform; the depth loads above are already in flight
+        __syncthreads();
+        f = fs;
+        have_f = true;
       }
-      if (h1) {
-        nvalid += backproject_quad(d1, i1 * 4u, W, wmagic, f, o, m);
-        float4* op = reinterpret_cast<float4*>(ofrm) + 3ll * i1;
-        __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
-        __stcs(op + 1, make_float4(o[4], o[5], o[6], o[7]));
-        __stcs(op + 2, make_float4(o[8], o[9], o[10], o[11]));
-        if (vfrm) __stcs(reinterpret_cast<uchar4*>(vfrm) + i1, m);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const unsigned iv = half ? i1 : i0;
+        const unsigned wbase = iv - lane;  // first float4 index of this warp's 32
+        if (wbase >= nvec) continue;       // warp-uniform
+        float o[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uchar4 m = make_uchar4(0, 0, 0, 0);
+        if (iv < nvec) nvalid += backproject_quad(half ? d1 : d0, iv * 4u, W, wmagic, f, o, m);
+        stage[warp][3 * lane] = make_float4(o[0], o[1], o[2], o[3]);
+        stage[warp][3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        stage[warp][3 * lane + 2] = make_float4(o[8], o[9], o[10], o[11]);
+        __syncwarp();
+        const float4 r0 = stage[warp][lane], r1 = stage[warp][lane + 32], r2 = stage[warp][lane + 64];
+        __syncwarp();
+        const unsigned nout = 3u * min(32u, nvec - wbase);  // float4s of this warp inside the frame
+        for (int p = 0; p < dst.n; ++p) {
+          float4* op = reinterpret_cast<float4*>(dst.xyz[p] + ooff) + 3ll * wbase;
+          if ((unsigned)lane < nout) __stcs(op + lane, r0);
+          if ((unsigned)lane + 32u < nout) __stcs(op + lane + 32, r1);
+          if ((unsigned)lane + 64u < nout) __stcs(op + lane + 64, r2);
+          if (has_valid && iv < nvec) __stcs(reinterpret_cast<uchar4*>(dst.valid[p] + voff) + iv, m);
+        }
       }
     }
   } else {
+    __syncthreads();
+    f = fs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
       const int v = (int)(i / W), u = (int)(i - (long long)v * W);
       float X, Y, Z;
-      const bool ok = backproject_one(dfrm[i], ((double)u - f.cx) * f.fx_inv, ((double)v - f.cy) * f.fy_inv, f, X, Y, Z);
-      ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
-      if (vfrm) vfrm[i] = ok ? 1 : 0;
+      double ray[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ray[c] = fma((double)u, f.dx[c], fma((double)v, f.dy[c], f.r0[c]));
+      const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z);
+      for (int p = 0; p < dst.n; ++p) {
+        float* ofrm = dst.xyz[p] + ooff;
+        ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
+        if (has_valid) dst.valid[p][voff + i] = ok ? 1 : 0;
+      }
       nvalid += ok ? 1 : 0;
     }
   }
-  if (counts) {
+  if (dst.counts[0]) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
     __shared__ int wsum[8];
@@ -131,38 +185,61 @@ __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __rest
     if (threadIdx.x == 0) {
       int s = 0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
-      if (s) atomicAdd(counts + b, s);
+      if (s)
+        for (int p = 0; p < dst.n; ++p) atomicAdd(dst.counts[p] + b, s);  // peer destinations: NVLink atomics
     }
   }
+}
+
+// xyz / valid / counts: n_dst destination pointers each (valid, counts: all NULL or all set), already offset to the
+// first frame this launch writes.
+int launch_backproject_multi(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
+                             float depth_scale, float depth_trunc, float* const* xyz, uint8_t* const* valid,
+                             int* const* counts, int n_dst, cudaStream_t stream) {
+  DAV2_CHECK(depth && xyz && K4 && B > 0 && H > 0 && W > 0, "backproject: null pointer or empty shape");
+  DAV2_CHECK(n_dst >= 1 && n_dst <= BP_MAX_DST, "backproject: 1..%d destinations", BP_MAX_DST);
+  DAV2_CHECK(depth_scale > 0.f, "backproject: depth_scale must be > 0");
+  const long long HW = (long long)H * W;
+  DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
+  BpDst dst;
+  bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  for (int p = 0; p < BP_MAX_DST; ++p) {
+    const bool on = p < n_dst;
+    dst.xyz[p] = on ? xyz[p] : nullptr;
+    dst.valid[p] = (on && valid) ? valid[p] : nullptr;
+    dst.counts[p] = (on && counts) ? counts[p] : nullptr;
+    if (on) {
+      DAV2_CHECK(dst.xyz[p] && (!valid || dst.valid[p]) && (!counts || dst.counts[p]), "backproject: null destination %d", p);
+      vec = vec && ((reinterpret_cast<uintptr_t>(dst.xyz[p]) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst.valid[p]) & 3) == 0);
+      // zero this launch's slice of every destination's count vector (peer pointers are mapped: stream-ordered memset)
+      if (dst.counts[p]) DAV2_CUDA_OK(cudaMemsetAsync(dst.counts[p], 0, sizeof(int) * B, stream));
+    }
+  }
+  dst.n = n_dst;
+  const double inv_scale = 1.0 / (double)depth_scale;
+  const double trunc = (double)depth_trunc;  // +inf disables truncation
+  // multiply-high division by W is exact for p < 2^32 / W  (p < HW); otherwise the kernel divides
+  const unsigned wmagic = (W > 1 && HW * (long long)W < (1ll << 32)) ? (unsigned)((1ull << 32) / (unsigned)W + 1ull) : 0u;
+  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
+  // one trip per block wherever the grid allows it: a block-stride loop with a fractional number of passes leaves
+  // most SMs idle during the last one (the first version: 3.5 passes)
+  if (bx > 1048576) bx = 1048576;
+  if (bx < 1) bx = 1;
+  ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (4.0 + n_dst * (valid ? 13.0 : 12.0)), stream);
+  dim3 grid((unsigned)bx, (unsigned)B);
+  if (vec)
+    backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
+  else
+    backproject_kernel<false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
+  DAV2_LAUNCH_OK();
+  return 0;
 }
 
 int launch_backproject(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
                        float depth_scale, float depth_trunc, float* xyz, uint8_t* valid, int* counts,
                        cudaStream_t stream) {
-  DAV2_CHECK(depth && xyz && K4 && B > 0 && H > 0 && W > 0, "backproject: null pointer or empty shape");
-  DAV2_CHECK(depth_scale > 0.f, "backproject: depth_scale must be > 0");
-  if (counts) DAV2_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * B, stream));
-  const long long HW = (long long)H * W;
-  DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
-  const double inv_scale = 1.0 / (double)depth_scale;
-  const double trunc = (double)depth_trunc;  // +inf disables truncation
-  const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(valid) & 3) == 0);
-  // multiply-high division by W is exact for p < 2^32 / W  (p < HW); otherwise the kernel divides
-  const unsigned wmagic = (W > 1 && HW * (long long)W < (1ll << 32)) ? (unsigned)((1ull << 32) / (unsigned)W + 1ull) : 0u;
-  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
-  // (bx * B) beyond ~16 waves of the 148 SMs x 3 resident CTAs buys nothing; the block-stride loop covers the rest
-  const long long cap = ((long long)sm_count() * 3 * 16 + B - 1) / B;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (valid ? 17.0 : 16.0), stream);
-  dim3 grid((unsigned)bx, (unsigned)B);
-  if (vec)
-    backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
-  else
-    backproject_kernel<false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, xyz, valid, counts);
-  DAV2_LAUNCH_OK();
-  return 0;
+  return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, &xyz, valid ? &valid : nullptr,
+                                  counts ? &counts : nullptr, 1, stream);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -183,41 +260,82 @@ struct MetricAcc {
   unsigned int n, na, nb, nc;
 };
 
+// true for finite x > 0 (one unsigned compare on the bit pattern; NaN, inf, zero and negatives fail)
+__device__ __forceinline__ bool pos_finite(float x) { return (__float_as_uint(x) - 1u) < 0x7f7fffffu; }
+
 template <int VARIANT>
+__device__ __forceinline__ bool metric_valid(float p, float g, float lo, float hi) {
+  if (VARIANT == 0) return (g >= lo) && (g <= hi);
+  if (VARIANT == 1) return (g > 0.f) && (p > 0.f) && !isinf(g) && !isinf(p);
+  return true;  // variants 2 / 3: every element counts (plain compute_errors / calculate_metrics(mask_invalid=False))
+}
+
+// EXACT = false: pred and gt of every counted pixel are finite and > 0, so t = max(g/p, p/g) < thr is evaluated as
+// (g < thr*p) && (p < thr*g) (equal up to the rounding of one quotient) and pred is neither NaN nor inf.
+// EXACT = true: the reference's literal formula (two IEEE divisions) for zero / negative / non-finite values.
+// (Two divisions + NaN bookkeeping on every pixel made the first version issue-bound: 80 % issue, 2.3 TB/s.)
+template <int VARIANT, bool EXACT>
 __device__ __forceinline__ void metric_accum(MetricAccF& a, float p, float g, float lo, float hi) {
-  bool ok;
-  if (VARIANT == 0)
-    ok = (g >= lo) && (g <= hi);
-  else if (VARIANT == 1)
-    ok = (g > 0.f) && (p > 0.f) && !isinf(g) && !isinf(p);
-  else
-    ok = true;  // variants 2 / 3: every element counts (plain compute_errors / calculate_metrics(mask_invalid=False))
   constexpr bool CM = (VARIANT == 1 || VARIANT == 3);  // calculate_metrics definitions
+  constexpr float A = CM ? 1.25f : 1.1f, B2 = 1.5625f, C3 = 1.953125f;
+  const bool ok = metric_valid<VARIANT>(p, g, lo, hi);
+  if (!ok) return;  // short body: compiled to predicated instructions, no divergence penalty beyond the predicate
   const float d = p - g;
   const float ad = fabsf(d);
-  const float t = fmaxf(g / p, p / g);
-  a.s_abs += ok ? ad : 0.f;
-  if (!CM) a.s_rel += ok ? ad / (g + 1e-6f) : 0.f;  // calculate_metrics divides the means instead
-  a.s_sq += ok ? d * d : 0.f;
-  a.s_gt += ok ? g : 0.f;
-  a.n += ok ? 1 : 0;
-  if (!CM) {
-    a.na += (ok && t < 1.1f) ? 1 : 0;
-    a.nb += (ok && isnan(p)) ? 1 : 0;  // eval/evaluation.py:33-36 NaN / Inf warnings
-    a.nc += (ok && isinf(p)) ? 1 : 0;
+  a.s_abs += ad;
+  if (!CM) {  // calculate_metrics divides the means instead
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(g + 1e-6f));  // <= 1 ulp; g + 1e-6 is a normal number here
+    a.s_rel = EXACT ? a.s_rel + ad / (g + 1e-6f) : fmaf(ad, r, a.s_rel);
+  }
+  a.s_sq = fmaf(d, d, a.s_sq);
+  a.s_gt += g;
+  a.n += 1;
+  bool ta, tb = false, tc = false;
+  if (!EXACT) {
+    ta = (g < A * p) && (p < A * g);
+    if (CM) {
+      tb = (g < B2 * p) && (p < B2 * g);
+      tc = (g < C3 * p) && (p < C3 * g);
+    }
   } else {
-    a.na += (ok && t < 1.25f) ? 1 : 0;
-    a.nb += (ok && t < 1.5625f) ? 1 : 0;
-    a.nc += (ok && t < 1.953125f) ? 1 : 0;
+    const float q0 = g / p, q1 = p / g;
+    const float t = fmaxf(q0, q1);
+    const bool tn = isnan(q0) || isnan(q1);  // torch.max / np.maximum propagate NaN, and NaN < thr is false
+    ta = !tn && t < A;
+    tb = !tn && t < B2;
+    tc = !tn && t < C3;
+  }
+  a.na += ta ? 1 : 0;
+  if (CM) {
+    a.nb += tb ? 1 : 0;
+    a.nc += tc ? 1 : 0;
+  } else if (EXACT) {
+    a.nb += isnan(p) ? 1 : 0;  // eval/evaluation.py:33-36 NaN / Inf warnings
+    a.nc += isinf(p) ? 1 : 0;
   }
 }
 
+// does any counted pixel of the quad need the literal formula?
 template <int VARIANT>
+__device__ __forceinline__ bool metric_needs_exact(const float4& p4, const float4& g4, float lo, float hi) {
+  if (VARIANT == 1) return false;  // the mask itself guarantees finite positive operands
+  const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+  bool need = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (VARIANT == 0) need |= metric_valid<0>(pp[k], gg[k], lo, hi) && !(pos_finite(pp[k]) && pos_finite(gg[k]));
+    else need |= !(pos_finite(pp[k]) && pos_finite(gg[k]));
+  }
+  return need;
+}
+
+template <int VARIANT, bool EXACT>
 __device__ __forceinline__ void metric_quad(MetricAccF& a, const float4& p4, const float4& g4, float lo, float hi) {
-  metric_accum<VARIANT>(a, p4.x, g4.x, lo, hi);
-  metric_accum<VARIANT>(a, p4.y, g4.y, lo, hi);
-  metric_accum<VARIANT>(a, p4.z, g4.z, lo, hi);
-  metric_accum<VARIANT>(a, p4.w, g4.w, lo, hi);
+  metric_accum<VARIANT, EXACT>(a, p4.x, g4.x, lo, hi);
+  metric_accum<VARIANT, EXACT>(a, p4.y, g4.y, lo, hi);
+  metric_accum<VARIANT, EXACT>(a, p4.z, g4.z, lo, hi);
+  metric_accum<VARIANT, EXACT>(a, p4.w, g4.w, lo, hi);
 }
 
 __device__ __forceinline__ void metric_fold(MetricAcc& a, const MetricAccF& c) {
@@ -237,28 +355,39 @@ __global__ void __launch_bounds__(256, 4) depth_metrics_kernel(const float* __re
   if (vec) {
     const long long nvec = HW >> 2;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // a block owns 512 consecutive float4 pairs per trip; four 16-byte loads are in flight per thread
-    for (long long base = (long long)blockIdx.x * 512; base < nvec; base += (long long)gridDim.x * 512) {
-      const long long i0 = base + threadIdx.x, i1 = i0 + 256;
+    // a block owns 1024 consecutive float4 pairs per pass and walks them in two trips of 512 (four 16-byte loads in
+    // flight per thread)
+    for (long long trip = (long long)blockIdx.x * 2; trip * 512 < nvec; trip = (trip & 1) ? trip + 2 * (long long)gridDim.x - 1 : trip + 1) {
+      const long long i0 = trip * 512 + threadIdx.x, i1 = i0 + 256;
       const bool h0 = i0 < nvec, h1 = i1 < nvec;
       float4 p0 = zero, g0 = zero, p1 = zero, g1 = zero;
       if (h0) { p0 = __ldcs(reinterpret_cast<const float4*>(pf) + i0); g0 = __ldcs(reinterpret_cast<const float4*>(gf) + i0); }
       if (h1) { p1 = __ldcs(reinterpret_cast<const float4*>(pf) + i1); g1 = __ldcs(reinterpret_cast<const float4*>(gf) + i1); }
       MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
-      if (h0) metric_quad<VARIANT>(c, p0, g0, lo, hi);
-      if (h1) metric_quad<VARIANT>(c, p1, g1, lo, hi);
+      // zero-filled (absent) quads are invalid under variants 0 / 1; variants 2 / 3 skip them explicitly
+      const bool exact = (h0 && metric_needs_exact<VARIANT>(p0, g0, lo, hi)) || (h1 && metric_needs_exact<VARIANT>(p1, g1, lo, hi));
+      if (!exact) {
+        if (h0) metric_quad<VARIANT, false>(c, p0, g0, lo, hi);
+        if (h1) metric_quad<VARIANT, false>(c, p1, g1, lo, hi);
+      } else {
+        if (h0) metric_quad<VARIANT, true>(c, p0, g0, lo, hi);
+        if (h1) metric_quad<VARIANT, true>(c, p1, g1, lo, hi);
+      }
       metric_fold(a, c);
     }
   } else {
     for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < HW; i0 += (long long)gridDim.x * blockDim.x * 8) {
       MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
-      for (long long i = i0; i < i0 + 8 && i < HW; ++i) metric_accum<VARIANT>(c, pf[i], gf[i], lo, hi);
+      for (long long i = i0; i < i0 + 8 && i < HW; ++i) metric_accum<VARIANT, true>(c, pf[i], gf[i], lo, hi);
       metric_fold(a, c);
     }
   }
-  double v[8] = {(double)a.n, a.s_abs, a.s_rel, a.s_sq, a.s_gt, (double)a.na, (double)a.nb, (double)a.nc};
+  // warp reduce: one REDUX per integer count, butterfly shuffles for the four fp64 sums
+  double v[8] = {(double)__reduce_add_sync(0xffffffffu, a.n), a.s_abs, a.s_rel, a.s_sq, a.s_gt,
+                 (double)__reduce_add_sync(0xffffffffu, a.na), (double)__reduce_add_sync(0xffffffffu, a.nb),
+                 (double)__reduce_add_sync(0xffffffffu, a.nc)};
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
+  for (int k = 1; k < 5; ++k)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
   __shared__ double sm[8][8];
@@ -285,8 +414,10 @@ int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW
              "depth_metrics: variant must be 0 (test_step mask), 1 (calculate_metrics), 2 (compute_errors, no mask) or 3 "
              "(calculate_metrics, no mask)");
   DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
-  long long bx = (HW / 4 + 511) / 512;
-  const long long cap = ((long long)sm_count() * 4 * 8 + B - 1) / B;
+  // every block makes (up to) two trips of 512 float4 pairs: the warp/block reduction and the 8 atomics are a fixed cost
+  // per block, and a whole number of trips avoids a mostly idle last pass
+  long long bx = (HW / 4 + 1023) / 1024;
+  const long long cap = 1048576;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   ProfScope ps(PC_METRICS, 0.0, (double)B * HW * 8.0, stream);

@@ -4,6 +4,7 @@ torch is used for device memory and streams only; every computation below is a h
 sm_100a kernel inside libdav2_b200.so.  All tensors must live on the GPU."""
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
@@ -146,6 +147,37 @@ def backproject(depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, dep
                                        float(depth_scale), float(depth_trunc), xyz.data_ptr(), _ptr(valid), _ptr(counts),
                                        current_stream_ptr(dev)), "dav2_backproject")
     return xyz, valid, counts
+
+
+def backproject_gather(depth: torch.Tensor, K4, T12, dst_xyz, dst_valid=None, dst_counts=None, frame_offset: int = 0,
+                       depth_scale: float = 1.0, depth_trunc: float = math.inf):
+    """Fused back-projection + all-gather store (dav2_backproject_gather): results for depth [B,H,W] are written at frame
+    index ``frame_offset + b`` of EVERY destination.  dst_* are lists of device pointers (ints; peer-mapped buffers from
+    ``sharding.CloudGather``) or of tensors ([F,H*W,3] fp32 / [F,H*W] u8 / [F] i32)."""
+    require_cuda(depth, "depth")
+    assert depth.dtype == torch.float32 and depth.dim() == 3
+    B, H, W = depth.shape
+    dev = depth.device
+    if not torch.is_tensor(K4):
+        K4 = torch.tensor([float(v) for v in K4], dtype=torch.float64)
+    K4 = K4.to(device=dev, dtype=torch.float64).contiguous()
+    k_per_frame = 1 if K4.dim() == 2 else 0
+    if T12 is not None:
+        T12 = T12.to(device=dev, dtype=torch.float64).contiguous()
+        assert T12.shape == (B, 12)
+    n = len(dst_xyz)
+    assert 1 <= n <= 8, "1..8 destinations"
+
+    def ptr_array(items):
+        if items is None:
+            return None
+        assert len(items) == n
+        return (C.c_void_p * n)(*[(t.data_ptr() if torch.is_tensor(t) else int(t)) for t in items])
+
+    check(_lib.load().dav2_backproject_gather(depth.data_ptr(), B, H, W, K4.data_ptr(), k_per_frame, _ptr(T12),
+                                              float(depth_scale), float(depth_trunc), ptr_array(dst_xyz), ptr_array(dst_valid),
+                                              ptr_array(dst_counts), n, int(frame_offset), current_stream_ptr(dev)),
+          "dav2_backproject_gather")
 
 
 def voxel_downsample(xyz: torch.Tensor, voxel_size: float, rgb: torch.Tensor | None = None,

@@ -93,6 +93,29 @@ int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const 
                      const double* T12, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
                      int32_t* counts, void* stream);
 
+/* Fused back-projection + point-cloud all-gather ("the kernel's output write is the collective").
+ * Same arithmetic as dav2_backproject, but every result is stored to n_dst (<= 8) destination buffers -- the gather
+ * buffers of all ranks, peer-mapped over NVLink (dav2_peer_*) -- at frame index frame_offset + b, so no separate
+ * all-gather runs afterwards.  xyz_dst / valid_dst / counts_dst are HOST arrays of n_dst device pointers to the BASE of
+ * each gathered buffer (xyz [world*B,H*W,3] fp32, valid [world*B,H*W] u8 or NULL array, counts [world*B] i32 or NULL
+ * array).  The caller orders readers after all writers with any later collective on the same streams (the metric
+ * all-reduce of the step does it) and double-buffers across steps. */
+int dav2_backproject_gather(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
+                            const double* T12, float depth_scale, float depth_trunc, float* const* xyz_dst,
+                            uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset,
+                            void* stream);
+
+/* Peer-mapped device buffers for dav2_backproject_gather: one process per GPU allocates its gather buffer
+ * (dav2_peer_alloc: cudaMalloc, so the allocation is IPC-exportable), exports a 64-byte handle (cudaIpcGetMemHandle),
+ * exchanges the handles through torch.distributed, and maps every other rank's buffer (dav2_peer_open:
+ * cudaIpcOpenMemHandle with lazy peer access).  Replaces the NCCL all_gather the reference path would otherwise need
+ * after depth_to_pointcloud.py:332-354 when the frames are sharded over GPUs. */
+int dav2_peer_alloc(void** ptr, int64_t bytes);
+int dav2_peer_free(void* ptr);
+int dav2_peer_export(const void* ptr, uint8_t* handle64);
+int dav2_peer_open(const uint8_t* handle64, void** ptr);
+int dav2_peer_close(void* ptr);
+
 /* Voxel-grid down-sample of a fused cloud: depth_to_pointcloud.py:357-359 (`combined.voxel_down_sample(voxel_size=0.01)`,
  * i.e. Open3D PointCloud::VoxelDownSample): voxel index = floor((p - (min_bound - voxel/2)) / voxel) per axis, one output
  * point per occupied voxel = the mean (accumulated in fp64) of its points, colours averaged the same way.

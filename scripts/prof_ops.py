@@ -40,6 +40,13 @@ if what in ("attn", "all"):
     qkv = rnd(M, 3 * D)
     for _ in range(reps):
         ops.attention_h16(qkv, 64, 1370, D)
+    if os.environ.get("DAV2_TIME"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20): ops.attention_h16(qkv, 64, 1370, D)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print("attention EMU=%s: %.3f ms  %.0f TFLOP/s" % (os.environ.get("DAV2_ATTN_EMU", "default"), ms, 4 * 64 * 16 * 1370 * 1370 * 64 / ms / 1e9))
 if what in ("geom",):
     B, H, W = 64, 518, 518
     depth = torch.rand(B, H, W, generator=g, device=dev) * 20.0
