@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdav2_b200.so")
+# DAV2_LIB_PATH: A/B an alternative build of the same library (profiling scripts only)
+LIB_PATH = os.environ.get("DAV2_LIB_PATH") or os.path.join(_HERE, "libdav2_b200.so")
 
 c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

@@ -4,12 +4,12 @@
 // softmax overlaps the other's tensor-core work.  256 threads = two warpgroups:
 //   WG0 warp 0      : TMA producer  - Q once, then K/V tiles through a 2-deep smem ring
 //   WG0 warp 1      : MMA issuer    - S = Q K^T (tcgen05, 128x128x64 -> TMEM cols [0,128)),
-//                                     O += P V (128x64x128 -> TMEM cols [128,192)), V is the
-//                                     MN-major B operand straight from the [token, 3D] qkv buffer
+//                                     O += P V (128x64x128 -> TMEM cols [128,192)); P is the A operand read from
+//                                     TMEM cols [192,256), V the MN-major B operand straight from the [token, 3D]
+//                                     qkv buffer
 //   WG0 warps 2,3   : idle (they only exist so that setmaxnreg can hand WG0's registers to WG1)
 //   WG1 warps 4..7  : softmax       - one query row per thread: tcgen05.ld S, online max / exp2 / sum in
-//                                     fp32, P -> h16 into 128B-swizzled smem (A operand of the PV MMA),
-//                                     O accumulates in TMEM (lazy rescale)
+//                                     fp32, P -> h16 pairs -> TMEM (tcgen05.st), O accumulates in TMEM (lazy rescale)
 // Softmax arithmetic (the bound of this kernel: 16 MUFU/clk/SM = 1024 cycles per 128x128 tile against 512
 // tensor-pipe cycles): packed fp32 (FFMA2/FADD2) for the scale-subtract and the row sums, and EMU of every 8
 // element pairs take their 2^x from a Cody-Waite + degree-3 polynomial on the FMA pipe instead of MUFU.EX2
@@ -33,7 +33,7 @@ struct AttnParams {
 };
 
 static constexpr int ATT_TILE = 128 * 64 * 2;  // 16 KB: one [128 x 64] h16 tile
-static constexpr int ATT_SMEM = 7 * ATT_TILE + 128;  // Q, K0, K1, V0, V1, P(2 tiles), barriers
+static constexpr int ATT_SMEM = 5 * ATT_TILE + 128;  // Q, K0, K1, V0, V1, barriers (P lives in TMEM)
 static constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -75,6 +75,25 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+// In-kernel timeline (profiling builds only, -DATTN_TRACE): clock64 stamps of one softmax lane and of the MMA issuer for
+// the CTAs of image 32 / head 8, 16 slots per (q-tile, kv-tile).
+#ifdef ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#define ATTN_STAMP(slot)                                                                                   \
+  do {                                                                                                     \
+    if (g_attn_trace && blockIdx.z == 32 && blockIdx.y == 8 && threadIdx.x == 128)                         \
+      g_attn_trace[((long long)blockIdx.x * p.nkv + j) * 16 + (slot)] = clock64();                         \
+  } while (0)
+#define ATTN_STAMP_M(slot)                                                                                 \
+  do {                                                                                                     \
+    if (g_attn_trace && blockIdx.z == 32 && blockIdx.y == 8 && threadIdx.x == 32)                          \
+      g_attn_trace[((long long)blockIdx.x * p.nkv + j) * 16 + (slot)] = clock64();                         \
+  } while (0)
+#else
+#define ATTN_STAMP(slot) do { } while (0)
+#define ATTN_STAMP_M(slot) do { } while (0)
+#endif
+
 template <bool FP16, int EMU>
 __global__ void __launch_bounds__(256, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
@@ -84,12 +103,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   const uint32_t sQ = base;
   const uint32_t sK = base + ATT_TILE;       // 2 stages
   const uint32_t sV = base + 3 * ATT_TILE;   // 2 stages
-  const uint32_t sP = base + 5 * ATT_TILE;   // 2 swizzle atoms (keys 0-63, 64-127)
-  const uint32_t bars = base + 7 * ATT_TILE;
-  const uint32_t BAR_Q = bars, BAR_KV_FULL = bars + 8, BAR_KV_EMPTY = bars + 24, BAR_S_FULL = bars + 40,
-                 BAR_S_EMPTY = bars + 48, BAR_P_FULL = bars + 56, BAR_O_FULL = bars + 64;
-  const uint32_t tmem_slot = bars + 72;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 7 * ATT_TILE + 72);
+  const uint32_t bars = base + 5 * ATT_TILE;
+  // K and V tiles have separate full/empty barriers: a K stage is free as soon as its S MMA has completed (the start of
+  // that tile's softmax), a V stage only after its PV MMA.  With one barrier pair per (K, V) stage the load of K(j+1)
+  // could not start before PV(j-1) had finished, and every tile exposed a full TMA latency in front of S(j+1).
+  const uint32_t BAR_Q = bars, BAR_K_FULL = bars + 8, BAR_K_EMPTY = bars + 24, BAR_V_FULL = bars + 40, BAR_V_EMPTY = bars + 56,
+                 BAR_S_FULL = bars + 72, BAR_S_EMPTY = bars + 80, BAR_P_FULL = bars + 88, BAR_O_FULL = bars + 96;
+  const uint32_t tmem_slot = bars + 104;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 5 * ATT_TILE + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -100,8 +121,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     prefetch_tmap(&tmQKV);
     mbar_init(BAR_Q, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR_KV_FULL + 8 * s, 1);
-      mbar_init(BAR_KV_EMPTY + 8 * s, 1);
+      mbar_init(BAR_K_FULL + 8 * s, 1);
+      mbar_init(BAR_K_EMPTY + 8 * s, 1);
+      mbar_init(BAR_V_FULL + 8 * s, 1);
+      mbar_init(BAR_V_EMPTY + 8 * s, 1);
     }
     mbar_init(BAR_S_FULL, 1);
     mbar_init(BAR_S_EMPTY, 128);
@@ -114,7 +137,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;  // S fp32 | O fp32 | P 16-bit pairs
 
   if (warp < 4) {
   setmaxnreg_dec<48>();
@@ -127,11 +150,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     __syncwarp();
     for (int j = 0; j < p.nkv; ++j) {
       const int s = j & 1;
-      mbar_wait(BAR_KV_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      mbar_wait(BAR_K_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(BAR_KV_FULL + 8 * s, 2 * ATT_TILE);
-        tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
-        tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_KV_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
+        mbar_expect_tx(BAR_K_FULL + 8 * s, ATT_TILE);
+        tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_K_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
+      }
+      __syncwarp();
+      mbar_wait(BAR_V_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(BAR_V_FULL + 8 * s, ATT_TILE);
+        tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_V_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
       }
       __syncwarp();
     }
@@ -141,20 +169,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     const uint32_t idesc_o = make_idesc_h(128, 64, 0, 1, p.fmt);   // O = P V   : V is MN-major
     const uint64_t qdesc = make_sw128_desc(sQ, 16, 1024);
     mbar_wait(BAR_Q, 0);
-    mbar_wait(BAR_KV_FULL, 0);
+    mbar_wait(BAR_K_FULL, 0);
     tc_fence_after();
     if (elect_one()) {
       const uint64_t kdesc = make_sw128_desc(sK, 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
       umma_commit(BAR_S_FULL);
+      umma_commit(BAR_K_EMPTY);
     }
     __syncwarp();
     for (int j = 0; j < p.nkv; ++j) {
       const int s = j & 1;
       if (j + 1 < p.nkv) {
         const int s1 = (j + 1) & 1;
-        mbar_wait(BAR_KV_FULL + 8 * s1, (uint32_t)((j + 1) >> 1) & 1u);
+        ATTN_STAMP_M(8);
+        mbar_wait(BAR_K_FULL + 8 * s1, (uint32_t)((j + 1) >> 1) & 1u);
+        ATTN_STAMP_M(9);
         mbar_wait(BAR_S_EMPTY, (uint32_t)j & 1u);  // softmax has pulled S(j) into registers
         tc_fence_after();
         if (elect_one()) {
@@ -162,20 +193,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
           umma_commit(BAR_S_FULL);
+          umma_commit(BAR_K_EMPTY + 8 * s1);
         }
         __syncwarp();
       }
+      mbar_wait(BAR_V_FULL + 8 * s, (uint32_t)(j >> 1) & 1u);
+      ATTN_STAMP_M(10);
       mbar_wait(BAR_P_FULL, (uint32_t)j & 1u);  // P(j) in smem, any rescale of O finished
+      ATTN_STAMP_M(11);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * ATT_TILE + (k & 3) * 32, 16, 1024);
+        for (int k = 0; k < 8; ++k) {  // 16 keys per MMA = 8 TMEM columns of P
           const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
-          umma_h16(tO, pdesc, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
+          umma_h16_ts(tO, tP + 8u * k, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
         }
         umma_commit(BAR_O_FULL);
-        umma_commit(BAR_KV_EMPTY + 8 * s);
+        umma_commit(BAR_V_EMPTY + 8 * s);
+        ATTN_STAMP_M(12);
       }
       __syncwarp();
     }
@@ -193,14 +228,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
     uint32_t sreg[128];
+    uint32_t s_ready = mbar_try_wait(BAR_S_FULL, 0u);
 
     for (int j = 0; j < p.nkv; ++j) {
       const int nvalid = p.N - j * 128;  // keys of this tile inside the image (>= 1)
-      mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
+      ATTN_STAMP(0);
+      if (!s_ready) mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
+      ATTN_STAMP(1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+      // PV(j-1) done <=> O may be rescaled and the P columns rewritten.  The probe's ~100-cycle latency hides behind the
+      // TMEM load; only a miss falls into the blocking wait below.
+      uint32_t o_ready = (j == 0) ? 1u : mbar_try_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);
       tmem_ld_wait();
+      ATTN_STAMP(2);
       tc_fence_before();
       mbar_arrive(BAR_S_EMPTY);  // S(j) is in registers: the issuer may overwrite the TMEM buffer with S(j+1)
       if (nvalid < 128) {        // warp-uniform: tail tile, keys beyond the image never contribute
@@ -208,29 +250,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         for (int i = 0; i < 128; ++i)
           if (i >= nvalid) sreg[i] = 0xff800000u;  // -inf
       }
-      // four independent chains (a single running max / sum is a 64-deep dependent chain: 'wait' stalls in ncu)
-      float mx0 = __uint_as_float(sreg[0]), mx1 = __uint_as_float(sreg[1]), mx2 = __uint_as_float(sreg[2]),
-            mx3 = __uint_as_float(sreg[3]);
+      // eight independent chains (a single running max is a 64-deep dependent chain: 'wait' stalls in ncu)
+      float mxc[8];
 #pragma unroll
-      for (int i = 4; i < 124; i += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(sreg[i + 2]), __uint_as_float(sreg[i + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(sreg[i + 4]), __uint_as_float(sreg[i + 5]));
-        mx3 = fmax3(mx3, __uint_as_float(sreg[i + 6]), __uint_as_float(sreg[i + 7]));
-      }
-      mx0 = fmax3(mx0, __uint_as_float(sreg[124]), __uint_as_float(sreg[125]));
-      mx1 = fmax3(mx1, __uint_as_float(sreg[126]), __uint_as_float(sreg[127]));
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      bool o_waited = false;
+      for (int c = 0; c < 8; ++c) mxc[c] = fmaxf(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
+#pragma unroll
+      for (int i = 16; i < 128; i += 16)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxc[c] = fmax3(mxc[c], __uint_as_float(sreg[i + 2 * c]), __uint_as_float(sreg[i + 2 * c + 1]));
+      const float mx = fmaxf(fmax3(mxc[0], mxc[1], mxc[2]), fmaxf(fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
+      ATTN_STAMP(3);
       if (j == 0) {
         m_ref = mx;
       } else {
         const float m_new = fmaxf(m_ref, mx);
         const bool need = (m_new - m_ref) * LOG2E > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) has finished accumulating into O
+          if (!o_ready) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) has finished accumulating into O
+          o_ready = 1u;
           tc_fence_after();
-          o_waited = true;
           const float alpha = need ? fast_exp2((m_ref - m_new) * LOG2E) : 1.0f;
           if (need) m_ref = m_new;
           l *= alpha;
@@ -247,6 +285,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
           tc_fence_before();
         }
       }
+      ATTN_STAMP(4);
       const float mscaled = m_ref * LOG2E;
       const float2 l2e2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mscaled, -mscaled);
       float2 rs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -265,20 +304,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         preg[i] = FP16 ? pack2<FMT_F16>(e.x, e.y) : pack2<FMT_BF16>(e.x, e.y);
       }
       l += ((rs[0].x + rs[0].y) + (rs[1].x + rs[1].y)) + ((rs[2].x + rs[2].y) + (rs[3].x + rs[3].y));
-      if (j > 0 && !o_waited) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P buffer
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t rowbase = sP + (uint32_t)(c >> 1) * ATT_TILE + (uint32_t)r * 128u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t chunk = (uint32_t)((c & 1) * 4 + g) ^ ((uint32_t)r & 7u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + chunk * 16u), "r"(preg[c * 16 + 4 * g]),
-                       "r"(preg[c * 16 + 4 * g + 1]), "r"(preg[c * 16 + 4 * g + 2]), "r"(preg[c * 16 + 4 * g + 3])
-                       : "memory");
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor-core (async) proxy
+      ATTN_STAMP(5);
+      if (!o_ready) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P columns
+      tc_fence_after();
+      ATTN_STAMP(6);
+      // P (16-bit pairs: column i of row r = keys 2i, 2i+1) goes straight into TMEM as the A operand of the PV MMA: one
+      // tcgen05.st burst instead of sixteen swizzled st.shared + a generic->async proxy fence (~370 cycles per tile in
+      // the in-kernel timeline), and the MMA no longer reads 32 KB of P per tile through shared memory.
+      tmem_st32(tP + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&preg[0]));
+      tmem_st32(tP + lane_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&preg[32]));
+      // probe S(j+1) while the stores drain
+      s_ready = (j + 1 < p.nkv) ? mbar_try_wait(BAR_S_FULL, (uint32_t)(j + 1) & 1u) : 0u;
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(BAR_P_FULL);
+      ATTN_STAMP(7);
     }
     // final: O / l
     mbar_wait(BAR_O_FULL, (uint32_t)(p.nkv - 1) & 1u);
@@ -315,6 +355,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     tmem_dealloc(tmem_base, 256);
   }
 }
+
 
 int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo,
                      uint32_t v_sbo) {
@@ -359,4 +400,15 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   return 0;
 }
 
+#ifdef ATTN_TRACE
+int set_attn_trace(long long* ptr) {
+  DAV2_CUDA_OK(cudaMemcpyToSymbol(g_attn_trace, &ptr, sizeof(ptr)));
+  return 0;
+}
+#endif
+
 }  // namespace dav2
+
+#ifdef ATTN_TRACE
+extern "C" int dav2_debug_set_attn_trace(void* ptr) { return dav2::set_attn_trace((long long*)ptr); }
+#endif

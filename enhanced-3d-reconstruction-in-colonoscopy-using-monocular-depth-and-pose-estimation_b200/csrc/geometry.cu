@@ -260,9 +260,6 @@ struct MetricAcc {
   unsigned int n, na, nb, nc;
 };
 
-// true for finite x > 0 (one unsigned compare on the bit pattern; NaN, inf, zero and negatives fail)
-__device__ __forceinline__ bool pos_finite(float x) { return (__float_as_uint(x) - 1u) < 0x7f7fffffu; }
-
 template <int VARIANT>
 __device__ __forceinline__ bool metric_valid(float p, float g, float lo, float hi) {
   if (VARIANT == 0) return (g >= lo) && (g <= hi);
@@ -316,18 +313,19 @@ __device__ __forceinline__ void metric_accum(MetricAccF& a, float p, float g, fl
   }
 }
 
-// does any counted pixel of the quad need the literal formula?
+// Does any counted pixel of the quad need the literal formula?  Branch-free: bits(x) - 1 (unsigned) is below
+// 0x7f7fffff exactly for finite x > 0, so one running unsigned max over the counted operands decides.
 template <int VARIANT>
-__device__ __forceinline__ bool metric_needs_exact(const float4& p4, const float4& g4, float lo, float hi) {
-  if (VARIANT == 1) return false;  // the mask itself guarantees finite positive operands
+__device__ __forceinline__ unsigned metric_exact_key(const float4& p4, const float4& g4, float lo, float hi) {
+  if (VARIANT == 1) return 0u;  // the mask itself guarantees finite positive operands
   const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
-  bool need = false;
+  unsigned key = 0u;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (VARIANT == 0) need |= metric_valid<0>(pp[k], gg[k], lo, hi) && !(pos_finite(pp[k]) && pos_finite(gg[k]));
-    else need |= !(pos_finite(pp[k]) && pos_finite(gg[k]));
+    const unsigned kk = max(__float_as_uint(pp[k]) - 1u, __float_as_uint(gg[k]) - 1u);
+    key = max(key, (VARIANT == 0 && !metric_valid<0>(pp[k], gg[k], lo, hi)) ? 0u : kk);
   }
-  return need;
+  return key;
 }
 
 template <int VARIANT, bool EXACT>
@@ -365,7 +363,7 @@ __global__ void __launch_bounds__(256, 4) depth_metrics_kernel(const float* __re
       if (h1) { p1 = __ldcs(reinterpret_cast<const float4*>(pf) + i1); g1 = __ldcs(reinterpret_cast<const float4*>(gf) + i1); }
       MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
       // zero-filled (absent) quads are invalid under variants 0 / 1; variants 2 / 3 skip them explicitly
-      const bool exact = (h0 && metric_needs_exact<VARIANT>(p0, g0, lo, hi)) || (h1 && metric_needs_exact<VARIANT>(p1, g1, lo, hi));
+      const bool exact = max(h0 ? metric_exact_key<VARIANT>(p0, g0, lo, hi) : 0u, h1 ? metric_exact_key<VARIANT>(p1, g1, lo, hi) : 0u) >= 0x7f7fffffu;
       if (!exact) {
         if (h0) metric_quad<VARIANT, false>(c, p0, g0, lo, hi);
         if (h1) metric_quad<VARIANT, false>(c, p1, g1, lo, hi);

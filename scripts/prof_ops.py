@@ -36,8 +36,8 @@ if what in ("conv", "all"):
         if what == "conv":
             ops.conv3x3_h16(x1, w1, bias, x1, x1, 0, want_relu=True)  # RCU conv2: two skip adds + dual output
         ops.conv3x3_h16(x2, w2, bias2, None, None, 0)   # output_conv1 at 296^2, 256 -> 128
-if what in ("attn", "all"):
-    qkv = rnd(M, 3 * D)
+if what in ("attn", "all", "attntrace"):
+    qkv = rnd(M, 3 * D, scale=float(os.environ.get("DAV2_QKV_SCALE", "1.0")))
     for _ in range(reps):
         ops.attention_h16(qkv, 64, 1370, D)
     if os.environ.get("DAV2_TIME"):
@@ -47,6 +47,17 @@ if what in ("attn", "all"):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print("attention EMU=%s: %.3f ms  %.0f TFLOP/s" % (os.environ.get("DAV2_ATTN_EMU", "default"), ms, 4 * 64 * 16 * 1370 * 1370 * 64 / ms / 1e9))
+if what == "attntrace":
+    # in-kernel timeline (library built with -DATTN_TRACE, selected through DAV2_LIB_PATH)
+    import ctypes, numpy as np
+    from dav2_b200 import _lib
+    lib = _lib.load()
+    trace = torch.zeros(11 * 11 * 16, dtype=torch.int64, device=dev)
+    ops.attention_h16(qkv, 64, 1370, D); torch.cuda.synchronize()
+    lib.dav2_debug_set_attn_trace.argtypes = [ctypes.c_void_p]
+    assert lib.dav2_debug_set_attn_trace(trace.data_ptr()) == 0
+    ops.attention_h16(qkv, 64, 1370, D); torch.cuda.synchronize()
+    np.save("gpurun_out/attn_trace.npy", trace.cpu().numpy().reshape(11, 11, 16))
 if what in ("geom",):
     B, H, W = 64, 518, 518
     depth = torch.rand(B, H, W, generator=g, device=dev) * 20.0
