@@ -20,6 +20,7 @@ class Dav2Config(C.Structure):
 
 
 FMT_F16, FMT_BF16 = 0, 1  # tensor-core operand formats (== include/dav2_b200.h `precision` / `fmt`)
+FMT_F32 = 2               # dav2_config.precision only: the fp32 validation engine
 
 
 class Dav2Error(RuntimeError):

@@ -35,7 +35,7 @@ int dav2_create(dav2_model** out, const dav2_config* cfg) {
   DAV2_CHECK(cfg->embed_dim % 128 == 0 && cfg->embed_dim <= 1024 && cfg->embed_dim == cfg->num_heads * 64,
              "dav2_create: embed_dim=%d heads=%d unsupported (need D = 64*heads, multiple of 128, <= 1024)",
              cfg->embed_dim, cfg->num_heads);
-  DAV2_CHECK(cfg->precision == 0 || cfg->precision == 1, "dav2_create: precision must be 0 (fp16) or 1 (bf16)");
+  DAV2_CHECK(cfg->precision >= 0 && cfg->precision <= 2, "dav2_create: precision must be 0 (fp16), 1 (bf16) or 2 (fp32 validation engine)");
   DAV2_CHECK(cfg->features % 16 == 0 && cfg->depth > 0, "dav2_create: features=%d depth=%d unsupported", cfg->features, cfg->depth);
   for (int i = 0; i < 4; ++i)
     DAV2_CHECK(cfg->out_channels[i] % 8 == 0 && cfg->tap_layers[i] >= 0 && cfg->tap_layers[i] < cfg->depth,

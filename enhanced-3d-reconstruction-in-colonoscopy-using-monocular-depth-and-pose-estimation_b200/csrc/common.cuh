@@ -16,7 +16,7 @@ namespace dav2 {
 // per call): FMT_F16 = IEEE half (the reference's AMP '16-mixed' precision, configs/trainer/default.yaml:4),
 // FMT_BF16 = bfloat16.  The codes equal the UMMA a_format / b_format values for kind::f16.
 typedef uint16_t h16;
-enum { FMT_F16 = 0, FMT_BF16 = 1 };
+enum { FMT_F16 = 0, FMT_BF16 = 1, FMT_F32 = 2 };  // FMT_F32: engine-level only (fp32_path.cu), never a UMMA format
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing (host)

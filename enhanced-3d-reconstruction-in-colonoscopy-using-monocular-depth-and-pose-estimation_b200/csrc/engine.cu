@@ -33,34 +33,38 @@ static int upload_f32(const float* data, int64_t n, float** out) {
   return dev_upload(data, (size_t)n * 4, reinterpret_cast<void**>(out));
 }
 
-static int upload_h(const std::vector<h16>& v, h16** out) {
-  return dev_upload(v.data(), v.size() * 2, reinterpret_cast<void**>(out));
-}
-
-static std::vector<h16> to_h(int fmt, const float* d, int64_t n, float scale_first = 1.f, int64_t first = 0) {
-  std::vector<h16> v((size_t)n);
-  for (int64_t i = 0; i < n; ++i) v[(size_t)i] = f2h_host(i < first ? d[i] * scale_first : d[i], fmt);
+// Packed matrix weights are built in float in the kernel layout and then converted to the model's operand format:
+// 16-bit (fp16 / bf16) for the tensor-core engine, or left in fp32 for the fp32 validation engine (FMT_F32, fp32_path.cu).
+static std::vector<float> to_f(const float* d, int64_t n, float scale_first = 1.f, int64_t first = 0) {
+  std::vector<float> v((size_t)n);
+  for (int64_t i = 0; i < n; ++i) v[(size_t)i] = i < first ? d[i] * scale_first : d[i];
   return v;
 }
 
 // Conv2d weight [Cout, Cin, 3, 3] -> [Cout][tap*Cpad + c] (tap = ky*3+kx), zero padded to Cpad
-static std::vector<h16> pack_conv3x3(int fmt, const float* w, int Cout, int Cin, int Cpad) {
-  std::vector<h16> v((size_t)Cout * 9 * Cpad, f2h_host(0.f, fmt));
+static std::vector<float> pack_conv3x3(const float* w, int Cout, int Cin, int Cpad) {
+  std::vector<float> v((size_t)Cout * 9 * Cpad, 0.f);
   for (int n = 0; n < Cout; ++n)
     for (int c = 0; c < Cin; ++c)
-      for (int t = 0; t < 9; ++t)
-        v[((size_t)n * 9 + t) * Cpad + c] = f2h_host(w[((size_t)n * Cin + c) * 9 + t], fmt);
+      for (int t = 0; t < 9; ++t) v[((size_t)n * 9 + t) * Cpad + c] = w[((size_t)n * Cin + c) * 9 + t];
   return v;
 }
 
 // ConvTranspose2d weight [Cin, Cout, s, s] -> [(ky*s+kx)*Cout + co][ci]
-static std::vector<h16> pack_convT(int fmt, const float* w, int Cin, int Cout, int s) {
-  std::vector<h16> v((size_t)s * s * Cout * Cin);
+static std::vector<float> pack_convT(const float* w, int Cin, int Cout, int s) {
+  std::vector<float> v((size_t)s * s * Cout * Cin);
   for (int ci = 0; ci < Cin; ++ci)
     for (int co = 0; co < Cout; ++co)
-      for (int k = 0; k < s * s; ++k)
-        v[((size_t)k * Cout + co) * Cin + ci] = f2h_host(w[((size_t)ci * Cout + co) * s * s + k], fmt);
+      for (int k = 0; k < s * s; ++k) v[((size_t)k * Cout + co) * Cin + ci] = w[((size_t)ci * Cout + co) * s * s + k];
   return v;
+}
+
+// upload in the operand format; the result is typed h16* for the 16-bit engine and really float* when fmt == FMT_F32
+static int upload_w(int fmt, const std::vector<float>& v, h16** out) {
+  if (fmt == FMT_F32) return dev_upload(v.data(), v.size() * 4, reinterpret_cast<void**>(out));
+  std::vector<h16> h(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h[i] = f2h_host(v[i], fmt);
+  return dev_upload(h.data(), h.size() * 2, reinterpret_cast<void**>(out));
 }
 
 static bool shape_is(const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
@@ -82,7 +86,7 @@ Model::Model(const dav2_config& c) : cfg(c) {
   L = c.depth;
   heads = c.num_heads;
   F = c.features;
-  fmt = c.precision == 1 ? FMT_BF16 : FMT_F16;
+  fmt = c.precision == 2 ? FMT_F32 : (c.precision == 1 ? FMT_BF16 : FMT_F16);
   blk.resize(L);
   memset(blk.data(), 0, sizeof(BlockW) * L);
   memset(proj_w, 0, sizeof(proj_w)); memset(proj_b, 0, sizeof(proj_b));
@@ -136,6 +140,8 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
   int idx = 0, u = 0, c = 0;
   char tail[64];
   const int64_t Dl = D;
+  // input channels of a packed 3x3 filter: padded to the 64-wide K block for the tensor-core kernels only
+  auto cpad = [&](int c) { return fmt == FMT_F32 ? c : (c + 63) / 64 * 64; };
 
 #define STORE_F32(dst)                                    \
   do {                                                    \
@@ -147,7 +153,7 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
 #define STORE_H16(dst, vec)                              \
   do {                                                    \
     h16* _p = nullptr;                                   \
-    if (int rc = upload_h(vec, &_p)) return rc;        \
+    if (int rc = upload_w(fmt, vec, &_p)) return rc;    \
     owned.push_back(_p);                                  \
     dst = _p;                                             \
   } while (0)
@@ -162,9 +168,10 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
     STORE_F32(pos);
   } else if (K == "pretrained.patch_embed.proj.weight") {
     WANT_SHAPE(Dl, 3, 14, 14);
-    std::vector<h16> v((size_t)D * KP_PATCH, f2h_host(0.f, fmt));
+    const int kp = fmt == FMT_F32 ? 588 : KP_PATCH;  // the tensor-core GEMM wants K padded to the 64-wide block
+    std::vector<float> v((size_t)D * kp, 0.f);
     for (int d = 0; d < D; ++d)
-      for (int k = 0; k < 588; ++k) v[(size_t)d * KP_PATCH + k] = f2h_host(data[(size_t)d * 588 + k], fmt);
+      for (int k = 0; k < 588; ++k) v[(size_t)d * kp + k] = data[(size_t)d * 588 + k];
     STORE_H16(patch_w, v);
   } else if (K == "pretrained.patch_embed.proj.bias") {
     WANT_SHAPE(Dl);
@@ -188,7 +195,7 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
     else if (T == "attn.qkv.weight") {
       WANT_SHAPE(3 * Dl, Dl);
       // q rows pre-scaled by d_head^-1/2 = 1/8 (exact in h16/fp32): upstream scales q before q@k^T
-      STORE_H16(b.qkv_w, to_h(fmt, data, n, 0.125f, Dl * Dl));
+      STORE_H16(b.qkv_w, to_f(data, n, 0.125f, Dl * Dl));
     } else if (T == "attn.qkv.bias") {
       WANT_SHAPE(3 * Dl);
       std::vector<float> t(data, data + n);
@@ -198,53 +205,53 @@ int Model::set_weight(const char* key, const float* data, const int64_t* shape, 
       owned.push_back(p);
       b.qkv_b = p;
     }
-    else if (T == "attn.proj.weight") { WANT_SHAPE(Dl, Dl); STORE_H16(b.proj_w, to_h(fmt, data, n)); }
+    else if (T == "attn.proj.weight") { WANT_SHAPE(Dl, Dl); STORE_H16(b.proj_w, to_f(data, n)); }
     else if (T == "attn.proj.bias") { WANT_SHAPE(Dl); STORE_F32(b.proj_b); }
-    else if (T == "mlp.fc1.weight") { WANT_SHAPE(4 * Dl, Dl); STORE_H16(b.fc1_w, to_h(fmt, data, n)); }
+    else if (T == "mlp.fc1.weight") { WANT_SHAPE(4 * Dl, Dl); STORE_H16(b.fc1_w, to_f(data, n)); }
     else if (T == "mlp.fc1.bias") { WANT_SHAPE(4 * Dl); STORE_F32(b.fc1_b); }
-    else if (T == "mlp.fc2.weight") { WANT_SHAPE(Dl, 4 * Dl); STORE_H16(b.fc2_w, to_h(fmt, data, n)); }
+    else if (T == "mlp.fc2.weight") { WANT_SHAPE(Dl, 4 * Dl); STORE_H16(b.fc2_w, to_f(data, n)); }
     else if (T == "mlp.fc2.bias") { WANT_SHAPE(Dl); STORE_F32(b.fc2_b); }
     else { set_last_error("set_weight: unknown key %s", key); return -4; }
   } else if (sscanf(key, "depth_head.projects.%d.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 0 && idx < 4, "set_weight(%s): index", key);
     const int64_t oc = cfg.out_channels[idx];
-    if (!strcmp(tail, "weight")) { WANT_SHAPE(oc, Dl, 1, 1); STORE_H16(proj_w[idx], to_h(fmt, data, n)); }
+    if (!strcmp(tail, "weight")) { WANT_SHAPE(oc, Dl, 1, 1); STORE_H16(proj_w[idx], to_f(data, n)); }
     else { WANT_SHAPE(oc); STORE_F32(proj_b[idx]); }
   } else if (sscanf(key, "depth_head.resize_layers.%d.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx == 0 || idx == 1 || idx == 3, "set_weight(%s): index", key);
     const int64_t oc = cfg.out_channels[idx];
     if (!strcmp(tail, "bias")) { WANT_SHAPE(oc); STORE_F32(rs_b[idx]); }
-    else if (idx == 3) { WANT_SHAPE(oc, oc, 3, 3); STORE_H16(rs_w[3], pack_conv3x3(fmt, data, (int)oc, (int)oc, (int)oc)); }
+    else if (idx == 3) { WANT_SHAPE(oc, oc, 3, 3); STORE_H16(rs_w[3], pack_conv3x3(data, (int)oc, (int)oc, (int)oc)); }
     else {
       const int s = idx == 0 ? 4 : 2;
       WANT_SHAPE(oc, oc, s, s);
-      STORE_H16(rs_w[idx], pack_convT(fmt, data, (int)oc, (int)oc, s));
+      STORE_H16(rs_w[idx], pack_convT(data, (int)oc, (int)oc, s));
     }
   } else if (sscanf(key, "depth_head.scratch.layer%d_rn.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 1 && idx <= 4 && !strcmp(tail, "weight"), "set_weight(%s): bad key", key);
     const int64_t oc = cfg.out_channels[idx - 1];
     WANT_SHAPE(F, oc, 3, 3);
-    STORE_H16(rn_w[idx - 1], pack_conv3x3(fmt, data, F, (int)oc, (int)((oc + 63) / 64 * 64)));
+    STORE_H16(rn_w[idx - 1], pack_conv3x3(data, F, (int)oc, cpad((int)oc)));
   } else if (sscanf(key, "depth_head.scratch.refinenet%d.resConfUnit%d.conv%d.%63s", &idx, &u, &c, tail) == 4) {
     DAV2_CHECK(idx >= 1 && idx <= 4 && u >= 1 && u <= 2 && c >= 1 && c <= 2, "set_weight(%s): bad key", key);
     Fusion& f = ref[idx - 1];
     if (!strcmp(tail, "weight")) {
       WANT_SHAPE(F, F, 3, 3);
-      STORE_H16(f.rcu_w[u - 1][c - 1], pack_conv3x3(fmt, data, F, F, (F + 63) / 64 * 64));
+      STORE_H16(f.rcu_w[u - 1][c - 1], pack_conv3x3(data, F, F, cpad(F)));
     } else { WANT_SHAPE(F); STORE_F32(f.rcu_b[u - 1][c - 1]); }
   } else if (sscanf(key, "depth_head.scratch.refinenet%d.out_conv.%63s", &idx, tail) == 2) {
     DAV2_CHECK(idx >= 1 && idx <= 4, "set_weight(%s): bad key", key);
-    if (!strcmp(tail, "weight")) { WANT_SHAPE(F, F, 1, 1); STORE_H16(ref[idx - 1].out_w, to_h(fmt, data, n)); }
+    if (!strcmp(tail, "weight")) { WANT_SHAPE(F, F, 1, 1); STORE_H16(ref[idx - 1].out_w, to_f(data, n)); }
     else { WANT_SHAPE(F); STORE_F32(ref[idx - 1].out_b); }
   } else if (K == "depth_head.scratch.output_conv1.weight") {
     WANT_SHAPE(F / 2, F, 3, 3);
-    STORE_H16(oc1_w, pack_conv3x3(fmt, data, F / 2, F, (F + 63) / 64 * 64));
+    STORE_H16(oc1_w, pack_conv3x3(data, F / 2, F, cpad(F)));
   } else if (K == "depth_head.scratch.output_conv1.bias") {
     WANT_SHAPE(F / 2);
     STORE_F32(oc1_b);
   } else if (K == "depth_head.scratch.output_conv2.0.weight") {
     WANT_SHAPE(32, F / 2, 3, 3);
-    STORE_H16(oc2_w, pack_conv3x3(fmt, data, 32, F / 2, (F / 2 + 63) / 64 * 64));
+    STORE_H16(oc2_w, pack_conv3x3(data, 32, F / 2, cpad(F / 2)));
   } else if (K == "depth_head.scratch.output_conv2.0.bias") {
     WANT_SHAPE(32);
     STORE_F32(oc2_b);
@@ -383,6 +390,7 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   DAV2_CHECK(weights_complete(&missing), "forward: weight '%s' was never loaded", missing.c_str());
   DAV2_CHECK(x && depth && B > 0, "forward: null pointer or empty batch");
   DAV2_CHECK(H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0, "forward: H=%d W=%d must be positive multiples of 14", H, W);
+  if (fmt == FMT_F32) return forward_fp32(x, B, H, W, depth, stream);
   const int ph = H / 14, pw = W / 14, P = ph * pw, N = P + 1;
   const int M = B * N, MP = B * P;
   const float* posT = nullptr;

@@ -31,7 +31,7 @@ struct DevBuf {
 struct Model {
   dav2_config cfg;
   int D, L, heads, F;
-  int fmt;  // FMT_F16 (default; the reference's AMP precision) or FMT_BF16
+  int fmt;  // FMT_F16 (default; the reference's AMP precision), FMT_BF16, or FMT_F32 (fp32 validation engine)
   // encoder
   h16* patch_w = nullptr;
   float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr;
@@ -59,6 +59,7 @@ struct Model {
   int set_pos_embed(int ph, int pw, const float* table);
   int buf(const char* name, size_t bytes, void** out);
   int forward(const float* x, int B, int H, int W, float* depth, cudaStream_t stream);
+  int forward_fp32(const float* x, int B, int H, int W, float* depth, cudaStream_t stream);  // fp32_path.cu
   int debug_buffer(const char* name, void** ptr, int64_t* bytes);
   int debug_read(const char* name, void* dst, int64_t bytes, cudaStream_t stream);
 };

@@ -98,8 +98,9 @@ class DepthAnythingV2(nn.Module):
     def __init__(self, encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024), use_bn=False,
                  use_clstoken=False, max_depth=20.0, precision="fp16"):
         super().__init__()
-        if precision not in ("fp16", "bf16"):
-            raise ValueError("precision must be 'fp16' (the reference's AMP 16-mixed; default) or 'bf16'")
+        if precision not in ("fp16", "bf16", "fp32"):
+            raise ValueError("precision must be 'fp16' (the reference's AMP 16-mixed; default), 'bf16', or 'fp32' "
+                             "(the slow all-fp32 validation engine of the 1e-4 parity gate)")
         self.precision = precision
         if encoder not in _ENCODERS:
             raise ValueError(f"unsupported encoder {encoder!r} (vits | vitb | vitl)")
@@ -148,7 +149,7 @@ class DepthAnythingV2(nn.Module):
         self._release()
         D, depth, heads, Fe, oc = self._cfg
         cfg = Dav2Config(D, depth, heads, Fe, (C.c_int32 * 4)(*oc), (C.c_int32 * 4)(*_TAPS[self.encoder]), float(self.max_depth),
-                         _lib.FMT_BF16 if self.precision == "bf16" else _lib.FMT_F16)
+                         {"fp16": _lib.FMT_F16, "bf16": _lib.FMT_BF16, "fp32": _lib.FMT_F32}[self.precision])
         h = C.c_void_p()
         with torch.cuda.device(device):
             check(lib.dav2_create(C.byref(h), C.byref(cfg)), "dav2_create")

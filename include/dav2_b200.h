@@ -40,7 +40,9 @@ typedef struct dav2_config {
   int32_t tap_layers[4];  /* 0-based block indices tapped for the DPT head     */
   float max_depth;        /* sigmoid scale, run.py:76 / configs/model/large.yaml:3 */
   int32_t precision;      /* tensor-core operand format: 0 = fp16 (the reference's AMP '16-mixed',
-                             configs/trainer/default.yaml:4), 1 = bf16; accumulation is always fp32 */
+                             configs/trainer/default.yaml:4), 1 = bf16; accumulation is always fp32.
+                             2 = fp32 validation engine: every contraction in fp32 SIMT arithmetic (the
+                             "fp32 mode" of the 1e-4 parity gate; ~100x slower, not the benchmarked path) */
 } dav2_config;
 
 int dav2_create(dav2_model** out, const dav2_config* cfg);
