@@ -288,6 +288,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);
 }
 
+// Two GELUs at once on the packed-fp32 pipe (FFMA2 / FMUL2): 18 instructions per pair instead of 30.  Same
+// Abramowitz-Stegun formula and constants as gelu_erf; the fc1 epilogue was issue bound with two epilogue warps per
+// SM sub-partition (ncu: 69 % tensor pipe, 50 % issue, XU 35 %).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 az = make_float2(fabsf(x.x) * 0.70710678118654752440f, fabsf(x.y) * 0.70710678118654752440f);
+  const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), az, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  // -poly(t): the sign is folded into the coefficients so that erf = fma(npoly, e, 1)
+  float2 np = __ffma2_rn(t, make_float2(-1.061405429f, -1.061405429f), make_float2(1.453152027f, 1.453152027f));
+  np = __ffma2_rn(np, t, make_float2(-1.421413741f, -1.421413741f));
+  np = __ffma2_rn(np, t, make_float2(0.284496736f, 0.284496736f));
+  np = __ffma2_rn(np, t, make_float2(-0.254829592f, -0.254829592f));
+  np = __fmul2_rn(np, t);
+  const float2 arg = __fmul2_rn(__fmul2_rn(az, make_float2(-1.4426950408889634f, -1.4426950408889634f)), az);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+  const float2 erf_abs = __ffma2_rn(np, e, make_float2(1.0f, 1.0f));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 ahx = __fmul2_rn(az, make_float2(0.70710678118654752440f, 0.70710678118654752440f));  // |x| / 2
+  return __ffma2_rn(ahx, erf_abs, hx);
+}
+
 // ----------------------------------------------------------------------------------------------
 // host: TMA tensor-map encoding through the driver entry point (no -lcuda link dependency)
 // ----------------------------------------------------------------------------------------------

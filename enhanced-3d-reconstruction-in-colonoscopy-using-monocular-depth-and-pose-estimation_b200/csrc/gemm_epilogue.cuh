@@ -106,7 +106,8 @@ __device__ __forceinline__ void epi_chunk_store(const GemmParams& p, uint32_t (&
     float a0 = __uint_as_float(v[4 * j]) + b4.x, a1 = __uint_as_float(v[4 * j + 1]) + b4.y;
     float a2 = __uint_as_float(v[4 * j + 2]) + b4.z, a3 = __uint_as_float(v[4 * j + 3]) + b4.w;
     if constexpr (GELU) {
-      a0 = gelu_erf(a0); a1 = gelu_erf(a1); a2 = gelu_erf(a2); a3 = gelu_erf(a3);
+      const float2 g01 = gelu_erf2(make_float2(a0, a1)), g23 = gelu_erf2(make_float2(a2, a3));
+      a0 = g01.x; a1 = g01.y; a2 = g23.x; a3 = g23.y;
     } else if constexpr (MODE != GM_LINEAR_RESID && MODE != GM_PATCH) {
       a0 = fmaxf(a0, relu_floor); a1 = fmaxf(a1, relu_floor); a2 = fmaxf(a2, relu_floor); a3 = fmaxf(a3, relu_floor);
     }

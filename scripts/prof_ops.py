@@ -25,6 +25,17 @@ if what in ("gemm", "all"):
         ops.linear_h16(a, w_fc1, b_fc1, 1)          # fc1   87680 x 4096 x 1024 + GELU
         ops.linear_resid_(x, hid, w_fc2, b_d, gamma)  # fc2   87680 x 1024 x 4096 + residual
         ops.linear_resid_(x, a, w_proj, b_d, gamma)   # proj  87680 x 1024 x 1024 + residual
+    if os.environ.get("DAV2_TIME"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for name, fn, fl in (("qkv", lambda: ops.linear_h16(a, w_qkv, b_qkv, 0), 2.0 * M * 3 * D * D),
+                             ("fc1+gelu", lambda: ops.linear_h16(a, w_fc1, b_fc1, 1), 2.0 * M * 4 * D * D),
+                             ("fc2+resid", lambda: ops.linear_resid_(x, hid, w_fc2, b_d, gamma), 2.0 * M * 4 * D * D),
+                             ("proj+resid", lambda: ops.linear_resid_(x, a, w_proj, b_d, gamma), 2.0 * M * D * D)):
+            fn(); torch.cuda.synchronize(); e0.record()
+            for _ in range(10): fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print("%-10s %.3f ms  %.0f TFLOP/s" % (name, ms, fl / ms / 1e9))
 if what in ("conv", "all"):
     B = 64
     x1 = rnd(B, 148, 148, 256); w1 = ops.pack_conv3x3_weight(rnd(256, 256, 3, 3, scale=(9 * 256) ** -0.5))
