@@ -213,11 +213,24 @@ def main():
     rel = synth_rel_poses(B, dev, 5 + rank)
     k4 = torch.tensor(K518, dtype=torch.float64, device=dev)
     xyz = torch.empty(B, HW, 3, dtype=torch.float32, device=dev)
-    cloud_all = mask_all = fused = None
+    cloud_all = mask_all = fused = gather_note = None
     if world > 1 and not args.no_gather:
         if args.gather == "fused":
-            fused = sharding.CloudGather(B, HW, dev)  # peer-mapped gather buffers (CUDA IPC over NVLink), double buffered
-        else:
+            # peer-mapped gather buffers (CUDA IPC over NVLink), double buffered.  If peer mapping is unavailable on this
+            # box (IPC disabled, no P2P between some pair) EVERY rank falls back to the NCCL all-gather together.
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                fused = sharding.CloudGather(B, HW, dev)
+            except Exception as e:  # noqa: BLE001
+                gather_note = f"fused gather unavailable ({type(e).__name__}: {e}); NCCL all-gather used"
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                if fused is not None:
+                    fused.close(collective=False)  # a peer failed to map: do not wait for it
+                fused = None
+                gather_note = gather_note or "fused gather unavailable on a peer rank; NCCL all-gather used"
+        if fused is None:
             cloud_all = torch.empty(world, B, HW, 3, dtype=torch.float32, device=dev)
             mask_all = torch.empty(world, B, HW, dtype=torch.uint8, device=dev)
 
@@ -360,6 +373,7 @@ def main():
                                                    "peer-mapped buffers" if fused is not None else
                                                    "; NCCL all-reduce of sums + all-gather of clouds") if world > 1 else ""),
                    "encoder": args.encoder, "batch_per_gpu": B, "size": S,
+                   **({"gather_note": gather_note} if gather_note else {}),
                    "l2": f"inputs re-read every step are {B * 3 * HW * 4 / 1e6:.0f} MB and activations >10 GB, larger than the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -138,19 +138,21 @@ class CloudGather:
         if self.world > 1:
             dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=self.device), group=self.group)
 
-    def close(self):
+    def close(self, collective: bool = True):
+        """Unmap the peers and free the local buffer.  ``collective=False`` skips the barriers (error paths in which
+        not every rank owns a CloudGather); the caller must then know that no peer kernel can still write here."""
         if self._closed:
             return
         self._closed = True
         from . import _lib
         torch.cuda.synchronize(self.device)
-        if self.world > 1:
+        if self.world > 1 and collective:
             dist.barrier(group=self.group)  # nobody unmaps / frees while a peer kernel may still write
         self._mem = None
         with torch.cuda.device(self.device):
             for r, p in enumerate(self.peers):
                 if r != self.rank:
                     _lib.check(self._lib.dav2_peer_close(p), "dav2_peer_close")
-            if self.world > 1:
+            if self.world > 1 and collective:
                 dist.barrier(group=self.group)
             _lib.check(self._lib.dav2_peer_free(self.base), "dav2_peer_free")
