@@ -33,7 +33,7 @@ struct AttnParams {
 };
 
 static constexpr int ATT_TILE = 128 * 64 * 2;  // 16 KB: one [128 x 64] h16 tile
-static constexpr int ATT_SMEM = 5 * ATT_TILE + 128;  // Q, K0, K1, V0, V1, barriers (P lives in TMEM)
+// shared memory: Q (16 KB) + two K and two V stages of KV x 64 h16 + barriers (P lives in TMEM)
 static constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -94,23 +94,28 @@ __device__ long long* g_attn_trace = nullptr;
 #define ATTN_STAMP_M(slot) do { } while (0)
 #endif
 
-template <bool FP16, int EMU>
-__global__ void __launch_bounds__(256, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+// KV = keys per tile.  128: two CTAs per SM (TMEM: S 128 + O 64 + P 64 = 256 columns each).  64: THREE CTAs per SM
+// (S 64 + O 64 in one 128-column allocation, P in a second 32-column one: 480 of the 512 columns), i.e. three softmax
+// warps per SM sub-partition instead of two to hide each other's TMEM / barrier / MUFU latencies -- tensor memory, not
+// registers, is what limits the number of query tiles in flight.
+template <bool FP16, int EMU, int KV>
+__global__ void __launch_bounds__(256, KV == 64 ? 3 : 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  constexpr int KV_TILE = KV * 128;  // bytes of one [KV x 64] h16 tile
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) __trap();  // swizzle-128B tiles need 1024 B alignment
   const uint32_t sQ = base;
-  const uint32_t sK = base + ATT_TILE;       // 2 stages
-  const uint32_t sV = base + 3 * ATT_TILE;   // 2 stages
-  const uint32_t bars = base + 5 * ATT_TILE;
+  const uint32_t sK = base + ATT_TILE;                 // 2 stages
+  const uint32_t sV = base + ATT_TILE + 2 * KV_TILE;   // 2 stages
+  const uint32_t bars = base + ATT_TILE + 4 * KV_TILE;
   // K and V tiles have separate full/empty barriers: a K stage is free as soon as its S MMA has completed (the start of
   // that tile's softmax), a V stage only after its PV MMA.  With one barrier pair per (K, V) stage the load of K(j+1)
   // could not start before PV(j-1) had finished, and every tile exposed a full TMA latency in front of S(j+1).
   const uint32_t BAR_Q = bars, BAR_K_FULL = bars + 8, BAR_K_EMPTY = bars + 24, BAR_V_FULL = bars + 40, BAR_V_EMPTY = bars + 56,
                  BAR_S_FULL = bars + 72, BAR_S_EMPTY = bars + 80, BAR_P_FULL = bars + 88, BAR_O_FULL = bars + 96;
-  const uint32_t tmem_slot = bars + 104;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 5 * ATT_TILE + 104);
+  const uint32_t tmem_slot = bars + 104;  // two slots: main allocation, P allocation (KV = 64 only)
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + ATT_TILE + 4 * KV_TILE + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -119,6 +124,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQKV);
+    prefetch_tmap(&tmKV);
     mbar_init(BAR_Q, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR_K_FULL + 8 * s, 1);
@@ -132,15 +138,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     mbar_init(BAR_O_FULL, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) {
+    if (KV == 128) {
+      tmem_alloc(tmem_slot, 256);
+    } else {  // 128 + 32 columns (allocations are powers of two; 160 would round up to 256 and cost the third CTA)
+      tmem_alloc_hold(tmem_slot, 128);
+      tmem_alloc(tmem_slot + 4, 32);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;  // S fp32 | O fp32 | P 16-bit pairs
+  const uint32_t tmem_base = tmem_slot_ptr[0];
+  // S fp32 | O fp32 | P 16-bit pairs
+  const uint32_t tS = tmem_base, tO = tmem_base + KV, tP = KV == 128 ? tmem_base + 192 : tmem_slot_ptr[1];
 
   if (warp < 4) {
-  setmaxnreg_dec<48>();
+  setmaxnreg_dec<KV == 64 ? 40 : 48>();
   if (warp == 0) {
     // ---------------- TMA producer (whole warp, elected lane issues) ----------------
     if (elect_one()) {
@@ -152,20 +166,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       const int s = j & 1;
       mbar_wait(BAR_K_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(BAR_K_FULL + 8 * s, ATT_TILE);
-        tma_load_2d(sK + s * ATT_TILE, &tmQKV, BAR_K_FULL + 8 * s, p.D + h * 64, row0 + j * 128);
+        mbar_expect_tx(BAR_K_FULL + 8 * s, KV_TILE);
+        tma_load_2d(sK + s * KV_TILE, &tmKV, BAR_K_FULL + 8 * s, p.D + h * 64, row0 + j * KV);
       }
       __syncwarp();
       mbar_wait(BAR_V_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(BAR_V_FULL + 8 * s, ATT_TILE);
-        tma_load_2d(sV + s * ATT_TILE, &tmQKV, BAR_V_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * 128);
+        mbar_expect_tx(BAR_V_FULL + 8 * s, KV_TILE);
+        tma_load_2d(sV + s * KV_TILE, &tmKV, BAR_V_FULL + 8 * s, 2 * p.D + h * 64, row0 + j * KV);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (whole warp, elected lane issues) ----------------
-    const uint32_t idesc_s = make_idesc_h(128, 128, 0, 0, p.fmt);  // S = Q K^T : both K-major
+    const uint32_t idesc_s = make_idesc_h(128, KV, 0, 0, p.fmt);   // S = Q K^T : both K-major
     const uint32_t idesc_o = make_idesc_h(128, 64, 0, 1, p.fmt);   // O = P V   : V is MN-major
     const uint64_t qdesc = make_sw128_desc(sQ, 16, 1024);
     mbar_wait(BAR_Q, 0);
@@ -189,7 +203,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         mbar_wait(BAR_S_EMPTY, (uint32_t)j & 1u);  // softmax has pulled S(j) into registers
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t kdesc = make_sw128_desc(sK + s1 * ATT_TILE, 16, 1024);
+          const uint64_t kdesc = make_sw128_desc(sK + s1 * KV_TILE, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
           umma_commit(BAR_S_FULL);
@@ -204,8 +218,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 16 keys per MMA = 8 TMEM columns of P
-          const uint64_t vdesc = make_sw128_desc(sV + s * ATT_TILE + k * 2048, p.v_lbo, p.v_sbo);
+        for (int k = 0; k < KV / 16; ++k) {  // 16 keys per MMA = 8 TMEM columns of P
+          const uint64_t vdesc = make_sw128_desc(sV + s * KV_TILE + k * 2048, p.v_lbo, p.v_sbo);
           umma_h16_ts(tO, tP + 8u * k, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
         }
         umma_commit(BAR_O_FULL);
@@ -216,7 +230,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     }
   }
   } else {
-    setmaxnreg_inc<208>();
+    setmaxnreg_inc<KV == 64 ? 120 : 208>();
     // ---------------- softmax / output (one query row per thread) ----------------
     // The whole S row (128 fp32) is pulled into registers with ONE exposed TMEM round trip, which frees the
     // S buffer at once (the issuer overlaps S(j+1) with this tile's softmax).  O accumulates in TMEM across
@@ -227,17 +241,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     const int r = q * 32 + lane;  // row within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
-    uint32_t sreg[128];
+    uint32_t sreg[KV];
     uint32_t s_ready = mbar_try_wait(BAR_S_FULL, 0u);
 
     for (int j = 0; j < p.nkv; ++j) {
-      const int nvalid = p.N - j * 128;  // keys of this tile inside the image (>= 1)
+      const int nvalid = p.N - j * KV;  // keys of this tile inside the image (>= 1)
       ATTN_STAMP(0);
       if (!s_ready) mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
       ATTN_STAMP(1);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+      for (int c = 0; c < KV / 32; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
       // PV(j-1) done <=> O may be rescaled and the P columns rewritten.  The probe's ~100-cycle latency hides behind the
       // TMEM load; only a miss falls into the blocking wait below.
       uint32_t o_ready = (j == 0) ? 1u : mbar_try_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);
@@ -245,9 +259,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       ATTN_STAMP(2);
       tc_fence_before();
       mbar_arrive(BAR_S_EMPTY);  // S(j) is in registers: the issuer may overwrite the TMEM buffer with S(j+1)
-      if (nvalid < 128) {        // warp-uniform: tail tile, keys beyond the image never contribute
+      if (nvalid < KV) {         // warp-uniform: tail tile, keys beyond the image never contribute
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < KV; ++i)
           if (i >= nvalid) sreg[i] = 0xff800000u;  // -inf
       }
       // eight independent chains (a single running max is a 64-deep dependent chain: 'wait' stalls in ncu)
@@ -255,7 +269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 #pragma unroll
       for (int c = 0; c < 8; ++c) mxc[c] = fmaxf(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
 #pragma unroll
-      for (int i = 16; i < 128; i += 16)
+      for (int i = 16; i < KV; i += 16)
 #pragma unroll
         for (int c = 0; c < 8; ++c) mxc[c] = fmax3(mxc[c], __uint_as_float(sreg[i + 2 * c]), __uint_as_float(sreg[i + 2 * c + 1]));
       const float mx = fmaxf(fmax3(mxc[0], mxc[1], mxc[2]), fmaxf(fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
@@ -289,9 +303,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       const float mscaled = m_ref * LOG2E;
       const float2 l2e2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mscaled, -mscaled);
       float2 rs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      uint32_t preg[64];
+      uint32_t preg[KV / 2];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {  // pair i = keys 2i, 2i+1
+      for (int i = 0; i < KV / 2; ++i) {  // pair i = keys 2i, 2i+1
         const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[2 * i]), __uint_as_float(sreg[2 * i + 1])), l2e2, nm2);
         float2 e;
         if ((i & 7) < EMU) {
@@ -311,8 +325,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       // P (16-bit pairs: column i of row r = keys 2i, 2i+1) goes straight into TMEM as the A operand of the PV MMA: one
       // tcgen05.st burst instead of sixteen swizzled st.shared + a generic->async proxy fence (~370 cycles per tile in
       // the in-kernel timeline), and the MMA no longer reads 32 KB of P per tile through shared memory.
-      tmem_st32(tP + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&preg[0]));
-      tmem_st32(tP + lane_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&preg[32]));
+#pragma unroll
+      for (int c = 0; c < KV / 64; ++c) tmem_st32(tP + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&preg[c * 32]));
       // probe S(j+1) while the stores drain
       s_ready = (j + 1 < p.nkv) ? mbar_try_wait(BAR_S_FULL, (uint32_t)(j + 1) & 1u) : 0u;
       tmem_st_wait();
@@ -352,7 +366,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    if (KV == 128) {
+      tmem_dealloc(tmem_base, 256);
+    } else {
+      tmem_dealloc(tmem_base, 128);
+      tmem_dealloc(tmem_slot_ptr[1], 32);
+    }
   }
 }
 
@@ -360,39 +379,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo,
                      uint32_t v_sbo) {
   DAV2_CHECK(D % 64 == 0 && N > 0 && B > 0, "attention: bad shape B=%d N=%d D=%d", B, N, D);
-  CUtensorMap tm;
-  if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;
-  // pairs out of every 8 whose 2^x is emulated on the FMA pipe (tuned on B200; DAV2_ATTN_EMU overrides for profiling)
-  static int emu = -1;
+  // DAV2_ATTN_EMU: pairs out of every 8 whose 2^x is emulated on the FMA pipe; DAV2_ATTN_KV: keys per tile (128 or 64).
+  // Both were tuned on B200; the environment overrides exist for profiling only.
+  static int emu = -1, kv = 64;
+  constexpr int SMEM128 = ATT_TILE + 4 * 128 * 128 + 128, SMEM64 = ATT_TILE + 4 * 64 * 128 + 128;
   if (emu < 0) {
     const char* e = getenv("DAV2_ATTN_EMU");
     emu = e ? atoi(e) : 2;
-    DAV2_CHECK(emu == 0 || emu == 2 || emu == 3 || emu == 4, "DAV2_ATTN_EMU must be 0, 2, 3 or 4");
-#define DAV2_ATTN_CFG(F, E) \
-  DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM))
-    DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3); DAV2_ATTN_CFG(true, 4);
-    DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3); DAV2_ATTN_CFG(false, 4);
+    DAV2_CHECK(emu == 0 || emu == 2 || emu == 3, "DAV2_ATTN_EMU must be 0, 2 or 3");
+    const char* k = getenv("DAV2_ATTN_KV");
+    kv = k ? atoi(k) : 64;
+    DAV2_CHECK(kv == 64 || kv == 128, "DAV2_ATTN_KV must be 64 or 128");
+#define DAV2_ATTN_CFG(F, E)                                                                                                  \
+  DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128));     \
+  DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64))
+    DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3);
+    DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3);
 #undef DAV2_ATTN_CFG
   }
+  CUtensorMap tm, tmkv;
+  if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;
+  if (int rc = make_tmap_2d(&tmkv, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, (uint32_t)kv)) return rc;
   AttnParams p;
   p.out = out;
   p.N = N;
   p.D = D;
-  p.nkv = (N + 127) / 128;
+  p.nkv = (N + kv - 1) / kv;
   p.v_lbo = v_lbo;
   p.v_sbo = v_sbo;
   p.fmt = fmt;
   dim3 grid((N + 127) / 128, D / 64, B);
   ProfScope ps(PC_ATTN, 4.0 * B * (D / 64) * (double)N * N * 64.0, 2.0 * 4.0 * B * (double)N * D, stream);
-#define DAV2_ATTN_GO(E)                                                                   \
-  do {                                                                                    \
-    if (fmt == FMT_F16) attention_kernel<true, E><<<grid, 256, ATT_SMEM, stream>>>(tm, p); \
-    else attention_kernel<false, E><<<grid, 256, ATT_SMEM, stream>>>(tm, p);               \
+#define DAV2_ATTN_GO(E)                                                                                  \
+  do {                                                                                                   \
+    if (kv == 64) {                                                                                      \
+      if (fmt == FMT_F16) attention_kernel<true, E, 64><<<grid, 256, SMEM64, stream>>>(tm, tmkv, p);     \
+      else attention_kernel<false, E, 64><<<grid, 256, SMEM64, stream>>>(tm, tmkv, p);                   \
+    } else {                                                                                             \
+      if (fmt == FMT_F16) attention_kernel<true, E, 128><<<grid, 256, SMEM128, stream>>>(tm, tmkv, p);   \
+      else attention_kernel<false, E, 128><<<grid, 256, SMEM128, stream>>>(tm, tmkv, p);                 \
+    }                                                                                                    \
   } while (0)
   switch (emu) {
     case 0: DAV2_ATTN_GO(0); break;
     case 3: DAV2_ATTN_GO(3); break;
-    case 4: DAV2_ATTN_GO(4); break;
     default: DAV2_ATTN_GO(2); break;
   }
 #undef DAV2_ATTN_GO

@@ -136,6 +136,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+// first of several allocations by the same warp: keeps the allocation permit (the last one relinquishes it)
+__device__ __forceinline__ void tmem_alloc_hold(uint32_t smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
