@@ -196,7 +196,12 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
   const int x1 = min(x0 + 1, Wi - 1);
   const float wx = fx - (float)x0;
   const h16* base = in + (long long)b * Hi * Wi * C;
-  // BILINEAR_ROWS output rows per thread: enough work per block to stay off the block-launch-rate limit
+  // BILINEAR_ROWS output rows per thread: enough work per block to stay off the block-launch-rate limit.  The two input
+  // rows of an output row are kept in registers and reused while the source row index does not move (an up-sample
+  // advances it by 0 or 1 per output row): 4 x 16-byte loads per output vector made the kernel L1-bandwidth bound
+  // (29 GB of L1 reads for 7.3 GB written per step, 3.5 TB/s); vertical reuse cuts the loads ~2.5x.
+  uint4 p00, p01, p10, p11;
+  int y0_prev = -2, y1_prev = -2;
 #pragma unroll
   for (int rr = 0; rr < BILINEAR_ROWS; ++rr) {
     const int yo = blockIdx.y * BILINEAR_ROWS + rr;
@@ -205,10 +210,26 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
     const int y0 = min((int)fy, Hi - 1);
     const int y1 = min(y0 + 1, Hi - 1);
     const float wy = fy - (float)y0;
-    const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
-    const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
-    const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
-    const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
+    if (y0 != y0_prev) {  // block-uniform
+      if (y0 == y1_prev) {
+        p00 = p10;
+        p01 = p11;
+      } else {
+        p00 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * C) + cv);
+        p01 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * C) + cv);
+      }
+    }
+    if (y1 != y1_prev) {
+      if (y1 == y0) {
+        p10 = p00;
+        p11 = p01;
+      } else {
+        p10 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * C) + cv);
+        p11 = __ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * C) + cv);
+      }
+    }
+    y0_prev = y0;
+    y1_prev = y1;
     const uint32_t* a = &p00.x;
     const uint32_t* bq = &p01.x;
     const uint32_t* c = &p10.x;
