@@ -139,6 +139,24 @@ def cpu_reference_frames(encoder, size, state_dict, n_warm, n_timed, budget_s=No
     return times, cores, torch.get_num_threads()
 
 
+def workload_config(args, world=1, gather=None, gather_note=None):
+    """The `config` object shared by both arms (BASELINE configs[2] on one GPU, the same per GPU for N > 1)."""
+    B, S = args.batch, args.size
+    multi = ""
+    if world > 1:
+        multi = ("; NCCL all-reduce of sums; clouds gathered by the back-projection kernel's stores into peer-mapped buffers"
+                 if gather == "fused" else "; NCCL all-reduce of sums + all-gather of clouds" if gather == "nccl" else
+                 "; NCCL all-reduce of sums")
+    cfg = {"workload": f"BASELINE configs[2]: DepthAnythingV2 {args.encoder} batch {B}/GPU, {S}x{S} synthetic SimCol-shaped "
+                       "frames, random-init weights; depth + pose chain + fused back-projection/SE(3)/validity + metric "
+                       "partial sums" + multi,
+           "encoder": args.encoder, "batch_per_gpu": B, "size": S,
+           "l2": f"inputs re-read every step are {B * 3 * S * S * 4 / 1e6:.0f} MB and activations >10 GB, larger than the 126 MB L2"}
+    if gather_note:
+        cfg["gather_note"] = gather_note
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -152,8 +170,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DepthAnythingV2 {args.encoder} {args.size}x{args.size} depth + point cloud, CPU reference path",
-                   "encoder": args.encoder, "size": args.size},
+        "config": workload_config(args),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample, "host_cores": cores},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -340,6 +357,7 @@ def main():
     h2d = B * 3 * HW * 4 + B * HW * 4
     d2h = 8 * 8 + 4 * B
 
+    fused_used = fused is not None
     if fused is not None:
         fused.close()
     if rank != 0:
@@ -367,14 +385,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16" if args.precision == "fp16" else "bf16",
         "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[2]: DepthAnythingV2 {args.encoder} batch {B}/GPU, {S}x{S} synthetic SimCol-shaped "
-                               "frames, random-init weights; depth + pose chain + fused back-projection/SE(3)/validity + metric "
-                               "partial sums" + (("; NCCL all-reduce of sums; clouds gathered by the back-projection kernel's stores into "
-                                                   "peer-mapped buffers" if fused is not None else
-                                                   "; NCCL all-reduce of sums + all-gather of clouds") if world > 1 else ""),
-                   "encoder": args.encoder, "batch_per_gpu": B, "size": S,
-                   **({"gather_note": gather_note} if gather_note else {}),
-                   "l2": f"inputs re-read every step are {B * 3 * HW * 4 / 1e6:.0f} MB and activations >10 GB, larger than the 126 MB L2"},
+        "config": workload_config(args, world, None if (world == 1 or args.no_gather) else ("fused" if fused_used else "nccl"),
+                                  gather_note),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "pinned host frames+gt -> H2D (double buffered on a copy stream) -> dav2 API -> D2H metric sums + counts; clouds stay in HBM"},

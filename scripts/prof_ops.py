@@ -80,7 +80,9 @@ if what in ("geom",):
         ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 1, True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
-    for name, fn in (("backproject", lambda: ops.backproject(depth, (170.1677, 169.8526, 194.7248, 198.2624), T12, out_xyz=xyz)),
+    k4dev = torch.tensor([170.1677, 169.8526, 194.7248, 198.2624], dtype=torch.float64, device=dev)
+    T12 = T12.to(dev)
+    for name, fn in (("backproject", lambda: ops.backproject(depth, k4dev, T12, out_xyz=xyz)),
                      ("metrics0", lambda: ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False))):
         fn(); torch.cuda.synchronize()
         ev[0].record()

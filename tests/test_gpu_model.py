@@ -98,6 +98,34 @@ def test_batch_consistency_and_strict_false():
     assert all(("pretrained" in n) == n.startswith("pretrained.") for n, _ in m2.named_parameters())
 
 
+def test_full_size_batch_properties_vitl():
+    """BASELINE configs[2] at its real size (vitl, 64 frames of 518^2 -- too large for the CPU oracle): size-independent
+    properties instead.  (1) frames are independent: frames 0 / 31 / 63 of the batch equal the same frames run alone to
+    16-bit rounding noise; (2) permuting the batch permutes the output; (3) the fp32 engine agrees on one frame at its
+    own 1e-4 gate x the fp16 gate; (4) the output is finite, inside (0, max_depth) and non-degenerate."""
+    from dav2_b200 import weights
+    from dav2_b200.dpt import MODEL_CONFIGS, DepthAnythingV2
+    m = DepthAnythingV2(**MODEL_CONFIGS["vitl"], max_depth=20.0)
+    weights.randomize_(m, seed=0)
+    m = m.cuda().eval()
+    weights.calibrate_(m, "cuda")
+    x = O.synthetic_frames(64, 518, 518, seed=21).cuda()
+    whole = m(x)
+    assert whole.shape == (64, 518, 518) and torch.isfinite(whole).all()
+    assert float(whole.min()) > 0.0 and float(whole.max()) < 20.0 and float(whole.std()) > 0.5
+    for b in (0, 31, 63):
+        single = m(x[b:b + 1].contiguous())
+        assert float((single[0] - whole[b]).abs().max() / whole[b].abs().max()) < DEPTH_TOL, b
+    perm = torch.arange(63, -1, -1, device="cuda")
+    flipped = m(x[perm].contiguous())
+    assert float((flipped[perm] - whole).abs().max() / whole.abs().max()) < DEPTH_TOL
+    m32 = DepthAnythingV2(**MODEL_CONFIGS["vitl"], max_depth=20.0, precision="fp32")
+    m32.load_state_dict(m.state_dict())
+    m32 = m32.cuda().eval()
+    ref = m32(x[5:6].contiguous())
+    assert float((ref[0] - whole[5]).abs().max() / ref.abs().max()) < DEPTH_TOL
+
+
 def test_infer_image_matches_oracle():
     oracle, m = _build("vits", seed=6)
     rng = np.random.default_rng(0)
