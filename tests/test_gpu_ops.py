@@ -50,7 +50,7 @@ def test_linear_resid(M, N, K, dt):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,act", [
     (1, 8, 16, 64, 64, 0), (2, 19, 19, 256, 256, 2), (1, 37, 37, 48, 64, 0), (2, 74, 74, 128, 128, 0),
-    (1, 50, 45, 64, 32, 0), (1, 37, 41, 1024, 256, 0)])
+    (1, 50, 45, 64, 32, 0), (1, 37, 41, 1024, 256, 0), (2, 148, 148, 64, 64, 2)])
 @pytest.mark.parametrize("dt", H16)
 def test_conv3x3(B, H, W, Cin, Cout, act, dt):
     from dav2_b200 import ops
