@@ -137,6 +137,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(BAR_P_FULL, 128);
     mbar_init(BAR_O_FULL, 1);
     fence_mbar_init();
+    // The first loads (Q and both K / V stages) go out BEFORE the CTA-wide sync below: their latency then overlaps the
+    // TMEM allocation and the barrier round trip of the prologue (a CTA lives for only 11-22 KV tiles at 518^2).
+    mbar_expect_tx(BAR_Q, ATT_TILE);
+    tma_load_2d(sQ, &tmQKV, BAR_Q, h * 64, row0 + q0);
+    for (int j = 0; j < 2 && j < p.nkv; ++j) {
+      mbar_expect_tx(BAR_K_FULL + 8 * j, KV_TILE);
+      tma_load_2d(sK + j * KV_TILE, &tmKV, BAR_K_FULL + 8 * j, p.D + h * 64, row0 + j * KV);
+      mbar_expect_tx(BAR_V_FULL + 8 * j, KV_TILE);
+      tma_load_2d(sV + j * KV_TILE, &tmKV, BAR_V_FULL + 8 * j, 2 * p.D + h * 64, row0 + j * KV);
+    }
   }
   if (warp == 1) {
     if (KV == 128) {
@@ -156,13 +166,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   if (warp < 4) {
   setmaxnreg_dec<KV == 64 ? 40 : 48>();
   if (warp == 0) {
-    // ---------------- TMA producer (whole warp, elected lane issues) ----------------
-    if (elect_one()) {
-      mbar_expect_tx(BAR_Q, ATT_TILE);
-      tma_load_2d(sQ, &tmQKV, BAR_Q, h * 64, row0 + q0);
-    }
-    __syncwarp();
-    for (int j = 0; j < p.nkv; ++j) {
+    // ---------------- TMA producer (whole warp, elected lane issues); tiles 0 and 1 were issued in the prologue ----
+    for (int j = 2; j < p.nkv; ++j) {
       const int s = j & 1;
       mbar_wait(BAR_K_EMPTY + 8 * s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
       if (elect_one()) {
