@@ -80,7 +80,9 @@ __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, in
   return nvalid;
 }
 
-template <bool VEC4>
+// MULTI = false: one destination (dst.*[0]); the destination loop over a runtime count made the compiler keep eight sets
+// of predicated 64-bit address arithmetic alive in the single-destination kernel as well.
+template <bool VEC4, bool MULTI>
 __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __restrict__ depth, int H, int W, unsigned wmagic,
                                                              const double* __restrict__ K4, int k_per_frame,
                                                              const double* __restrict__ T12, double inv_scale,
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __rest
   const float* dfrm = depth + b * HW;
   const long long ooff = b * HW * 3, voff = b * HW;
   const bool has_valid = dst.valid[0] != nullptr;
+  const int ndst = MULTI ? dst.n : 1;
   int nvalid = 0;
   bool have_f = false;
   BpFrame f;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __rest
         const float4 r0 = stage[warp][lane], r1 = stage[warp][lane + 32], r2 = stage[warp][lane + 64];
         __syncwarp();
         const unsigned nout = 3u * min(32u, nvec - wbase);  // float4s of this warp inside the frame
-        for (int p = 0; p < dst.n; ++p) {
+        for (int p = 0; p < ndst; ++p) {
           float4* op = reinterpret_cast<float4*>(dst.xyz[p] + ooff) + 3ll * wbase;
           if ((unsigned)lane < nout) __stcs(op + lane, r0);
           if ((unsigned)lane + 32u < nout) __stcs(op + lane + 32, r1);
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __rest
 #pragma unroll
       for (int c = 0; c < 3; ++c) ray[c] = fma((double)u, f.dx[c], fma((double)v, f.dy[c], f.r0[c]));
       const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z);
-      for (int p = 0; p < dst.n; ++p) {
+      for (int p = 0; p < ndst; ++p) {
         float* ofrm = dst.xyz[p] + ooff;
         ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
         if (has_valid) dst.valid[p][voff + i] = ok ? 1 : 0;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __rest
       int s = 0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
       if (s)
-        for (int p = 0; p < dst.n; ++p) atomicAdd(dst.counts[p] + b, s);  // peer destinations: NVLink atomics
+        for (int p = 0; p < ndst; ++p) atomicAdd(dst.counts[p] + b, s);  // peer destinations: NVLink atomics
     }
   }
 }
@@ -227,10 +230,12 @@ int launch_backproject_multi(const float* depth, int B, int H, int W, const doub
   if (bx < 1) bx = 1;
   ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (4.0 + n_dst * (valid ? 13.0 : 12.0)), stream);
   dim3 grid((unsigned)bx, (unsigned)B);
-  if (vec)
-    backproject_kernel<true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
+  if (vec && n_dst == 1)
+    backproject_kernel<true, false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
+  else if (vec)
+    backproject_kernel<true, true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
   else
-    backproject_kernel<false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
+    backproject_kernel<false, true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
   DAV2_LAUNCH_OK();
   return 0;
 }
