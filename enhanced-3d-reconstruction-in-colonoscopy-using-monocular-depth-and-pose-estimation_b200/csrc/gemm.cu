@@ -65,7 +65,7 @@ int launch_gemm(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB
 
 template <int BN, int MODE>
 static int launch2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, gemm2_wide_epi(BN, MODE)>;
   static bool configured = false;
   if (!configured) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -80,15 +80,22 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN>
+// Sixteen epilogue warps (four per SM sub-partition, 64 accumulator columns each) for the 256-wide bias / GELU tile: with
+// eight, the fc1 + GELU epilogue could not keep pace with the MMA stream (ncu: 70 % tensor pipe, 50 % issue with two
+// warps per sub-partition; 81 % with four).  The LayerScale + residual mode keeps eight warps and the fifth smem stage:
+// its epilogue is light and its K = 4096 main loop wants the deeper ring (96 % -> 87 % with four stages).
+__host__ __device__ constexpr bool gemm2_wide_epi(int bn, int mode) { return bn == 256 && mode == GM_LINEAR_BF16; }
+
+template <int BN, bool WIDE>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * 64 * 2;          // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;     // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_WARPS = 8;                    // 2 per SM sub-partition: each TMEM lane quadrant is drained by two warps (column halves)
-  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES;  // 5 (BN=256) / 6 (BN=128)
+  static constexpr int EPI_WARPS = WIDE ? 16 : 8;        // 2 (4) per SM sub-partition: each TMEM lane quadrant is drained by two (four) warps
+  static constexpr int STAGES = WIDE ? 4 : (160 * 1024) / STAGE_BYTES;  // 5 (BN=256) / 6 (BN=128); 4 with the wide epilogue's staging
+  static constexpr int HN = BN / (EPI_WARPS / 4);        // accumulator columns drained per epilogue warp
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * ::dav2::STG_ROW_BYTES;
-  static constexpr int VEC_BYTES = EPI_WARPS * 2 * (BN / 2) * 4;  // per epilogue warp: bias[BN/2] | gamma[BN/2] of its column half
+  static constexpr int VEC_BYTES = EPI_WARPS * 2 * HN * 4;  // per epilogue warp: bias[HN] | gamma[HN] of its column slice
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
@@ -96,10 +103,10 @@ struct Gemm2Cfg {
 };
 
 template <int BN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * Gemm2Cfg<BN>::EPI_WARPS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * Gemm2Cfg<BN, gemm2_wide_epi(BN, MODE)>::EPI_WARPS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const GemmParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, gemm2_wide_epi(BN, MODE)>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool IS_CONV = (MODE == GM_CONV_BF16);
   static_assert(MODE != GM_CONV_HEAD, "the N=32 head stays on the 1-CTA kernel");
@@ -224,7 +231,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp >= 2) {
     // ================================ epilogue (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
-    constexpr int HN = BN / 2;                       // columns drained by this warp
+    constexpr int HN = Cfg::HN;                      // columns drained by this warp
     const int col0 = ((warp - 2) >> 2) * HN;           // warps 2..5 -> first half, 6..9 -> second half
     const uint32_t stg = staging + (uint32_t)(warp - 2) * 32u * STG_ROW_BYTES;
     const uint32_t vec = vecs + (uint32_t)(warp - 2) * (2 * HN * 4);
