@@ -6,8 +6,9 @@ names and state-dict keys of upstream, so ``run.py:120-149`` and ``lightning_mod
 work unchanged, but the arithmetic runs in libdav2_b200.so (tcgen05 GEMMs / implicit-GEMM convs,
 fused attention, ...).  One extra keyword, ``precision`` ("fp16" default = the reference's Lightning
 ``16-mixed`` AMP, configs/trainer/default.yaml:4; or "bf16"), picks the tensor-core operand format;
-accumulation, the residual stream, LayerNorm statistics and softmax are always fp32.  The ``nn`` layers below are PARAMETER CONTAINERS ONLY (they give the
-upstream parameter names and shapes); they are never called.  No CPU path exists: calling
+accumulation, the residual stream, LayerNorm statistics and softmax are always fp32.  ``precision="fp32"`` selects the
+slow all-fp32 validation engine (the 1e-4 parity gate).  The ``nn`` layers below are PARAMETER CONTAINERS ONLY (they give
+the upstream parameter names and shapes); they are never called.  No CPU path exists: calling
 ``forward`` with the module or input off the GPU raises.
 """
 from __future__ import annotations

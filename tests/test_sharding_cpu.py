@@ -84,3 +84,14 @@ def test_frame_range_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sharding.frame_range(4, 2, 2)
+
+
+def test_cloud_gather_needs_the_library_and_a_gpu():
+    """CloudGather is GPU-only plumbing: on a CPU box it must fail loudly (no silent fallback), and its layout maths
+    (256-byte aligned xyz | valid | counts sections, double buffered) is checkable without a device."""
+    from dav2_b200 import sharding
+    assert sharding._align(1) == 256 and sharding._align(256) == 256 and sharding._align(257) == 512
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            sharding.CloudGather(2, 16, "cuda")
