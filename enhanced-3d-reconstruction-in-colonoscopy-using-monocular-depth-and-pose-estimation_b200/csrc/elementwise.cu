@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
   const int x0 = min((int)fx, Wi - 1);
   const int x1 = min(x0 + 1, Wi - 1);
   const float wx = fx - (float)x0;
-  const long long rstride = (long long)Wi * c8;  // uint4 units between source rows
+  const int rstride = Wi * c8;  // uint4 units between source rows (one image: fits 32 bits, checked by the launcher)
   const uint4* col0 = reinterpret_cast<const uint4*>(in + ((long long)b * Hi * Wi + x0) * C) + cv;
   const uint4* col1 = reinterpret_cast<const uint4*>(in + ((long long)b * Hi * Wi + x1) * C) + cv;
   const int yo0 = blockIdx.y * BILINEAR_ROWS;
@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
   float top[8], bot[8];
   int yt = -2, yb = -2;  // source rows held in top / bot
   auto load_row = [&](int y, float (&dst)[8]) {
-    const uint4 pa = __ldg(col0 + y * rstride), pb = __ldg(col1 + y * rstride);
+    const int off = y * rstride;
+    const uint4 pa = __ldg(col0 + off), pb = __ldg(col1 + off);
     const uint32_t* a = &pa.x;
     const uint32_t* bq = &pb.x;
 #pragma unroll
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const h16* __restric
 int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int fmt, cudaStream_t stream) {
   DAV2_CHECK(C % 8 == 0, "bilinear: C=%d must be a multiple of 8", C);
   DAV2_CHECK(Ho <= 65535 && B <= 65535, "bilinear: Ho / B exceed the grid limits");
+  DAV2_CHECK((long long)Hi * Wi * (C / 8) < (1ll << 31), "bilinear: one source image exceeds 2^31 16-byte vectors");
   const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
