@@ -1,6 +1,7 @@
 """GPU baseline 'the kernel to beat' (SURVEY.md 8d): the oracle model (the reference's architecture in plain PyTorch)
 run eagerly on the same B200 with fp16 autocast + TF32, the reference's own GPU settings (configs/trainer/default.yaml:4,
-test_lightning.py:24).  Not part of the product or of bench.py; prints one JSON line for DESIGN.md."""
+test_lightning.py:24).  Not part of the product or of bench.py (it lives under tests/ because it executes the oracle); prints one JSON line
+for DESIGN.md.  Usage on the GPU box: python tests/gpu_eager_baseline.py [encoder] [batch] [size]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
