@@ -5,6 +5,8 @@
 // reduce-by-key of fp64 sums (values gathered on the fly through the sorted index) -> means.
 // Output order is ascending (ix, iy, iz); Open3D's is hash-map order, so results compare as sets.
 #include <cub/cub.cuh>
+
+#include <vector>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -129,6 +131,23 @@ int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* v
   Bounds empty;
   for (int k = 0; k < 3; ++k) { empty.lo[k] = INFINITY; empty.hi[k] = -INFINITY; }
 
+  // stream-ordered scratch, released on every exit path
+  struct Scratch {
+    cudaStream_t s;
+    std::vector<void*> p;
+    ~Scratch() {
+      for (void* q : p) cudaFreeAsync(q, s);
+    }
+    int get(void** out, size_t bytes) {
+      DAV2_CUDA_OK(cudaMallocAsync(out, bytes, s));
+      p.push_back(*out);
+      return 0;
+    }
+  } scratch{stream, {}};
+#define VOX_ALLOC(ptr, bytes)                                                    \
+  do {                                                                           \
+    if (int rc = scratch.get(reinterpret_cast<void**>(&(ptr)), (bytes))) return rc; \
+  } while (0)
   Bounds* bounds = nullptr;
   unsigned long long *keys = nullptr, *keys_s = nullptr;  // keys is reused for the unique keys after the sort
   unsigned int *idx = nullptr, *idx_s = nullptr;
@@ -137,14 +156,14 @@ int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* v
   int* overflow = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, need = 0;
-  DAV2_CUDA_OK(cudaMallocAsync(&bounds, sizeof(Bounds), stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&keys, n * 8, stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&keys_s, n * 8, stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&idx, n * 4, stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&idx_s, n * 4, stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&sums, n * sizeof(VoxAcc), stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&nruns, sizeof(long long), stream));
-  DAV2_CUDA_OK(cudaMallocAsync(&overflow, sizeof(int), stream));
+  VOX_ALLOC(bounds, sizeof(Bounds));
+  VOX_ALLOC(keys, n * 8);
+  VOX_ALLOC(keys_s, n * 8);
+  VOX_ALLOC(idx, n * 4);
+  VOX_ALLOC(idx_s, n * 4);
+  VOX_ALLOC(sums, n * sizeof(VoxAcc));
+  VOX_ALLOC(nruns, sizeof(long long));
+  VOX_ALLOC(overflow, sizeof(int));
   DAV2_CUDA_OK(cudaMemsetAsync(overflow, 0, sizeof(int), stream));
   BoundsIt bit(CountIt(0), PointBounds{xyz, valid});
   GatherIt git(idx_s, GatherAcc{xyz, rgb});
@@ -155,7 +174,8 @@ int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* v
   tmp_bytes = need > tmp_bytes ? need : tmp_bytes;
   DAV2_CUDA_OK(cub::DeviceReduce::ReduceByKey(nullptr, need, keys_s, keys, git, sums, nruns, VoxAdd(), (int)n, stream));
   tmp_bytes = need > tmp_bytes ? need : tmp_bytes;
-  DAV2_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, stream));
+  VOX_ALLOC(tmp, tmp_bytes);
+#undef VOX_ALLOC
 
   // bytes: bounds 12n, keys 12n+12n, sort ~4 passes x 24n, gather 12n(+12n) + keys 8n, outputs
   ProfScope ps(PC_OTHER, 0.0, (double)n * 160.0, stream);
@@ -169,8 +189,6 @@ int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* v
   DAV2_CUDA_OK(cub::DeviceReduce::ReduceByKey(tmp, tb, keys_s, keys, git, sums, nruns, VoxAdd(), (int)n, stream));
   vox_finalize<<<vgrid(n), 256, 0, stream>>>(keys, sums, nruns, overflow, out_xyz, out_rgb, out_count);
   DAV2_LAUNCH_OK();
-  for (void* p : {(void*)bounds, (void*)keys, (void*)keys_s, (void*)idx, (void*)idx_s, (void*)sums, (void*)nruns, (void*)overflow, tmp})
-    DAV2_CUDA_OK(cudaFreeAsync(p, stream));
   return 0;
 }
 
