@@ -388,7 +388,8 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   // Both were tuned on B200; the environment overrides exist for profiling only.
   static int emu = -1, kv = 64;
   constexpr int SMEM128 = ATT_TILE + 4 * 128 * 128 + 128, SMEM64 = ATT_TILE + 4 * 64 * 128 + 128;
-  if (emu < 0) {
+  static char tag;
+  if (first_use_on_device(&tag)) {
     const char* e = getenv("DAV2_ATTN_EMU");
     emu = e ? atoi(e) : 2;
     DAV2_CHECK(emu == 0 || emu == 2 || emu == 3, "DAV2_ATTN_EMU must be 0, 2 or 3");

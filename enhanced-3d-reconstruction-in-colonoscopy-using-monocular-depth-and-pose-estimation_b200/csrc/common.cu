@@ -3,6 +3,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <stdarg.h>
 #include <string.h>
 
@@ -75,6 +77,17 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
              (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, tw, th,
              (int)r);
   return 0;
+}
+
+// cudaFuncSetAttribute is per (function, device): `first_use_on_device(tag)` is true exactly once per device and tag
+// (tag = the address of a function-local static), also when several devices are driven from one process.
+bool first_use_on_device(const void* tag) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(std::make_pair(dev, tag)).second;
 }
 
 int sm_count() {

@@ -329,6 +329,7 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
                    uint32_t tw, uint32_t th);
 
 int sm_count();
+bool first_use_on_device(const void* tag);  // true once per (device, tag): per-device kernel attribute set-up
 
 }  // namespace dav2
 

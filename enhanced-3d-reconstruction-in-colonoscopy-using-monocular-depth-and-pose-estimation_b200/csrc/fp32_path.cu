@@ -215,11 +215,9 @@ static int attention_f32(const float* qkv, float* out, int B, int N, int D, cuda
   const int Npad = (N + 31) & ~31;
   const size_t smem = (size_t)4 * Npad * sizeof(float);
   DAV2_CHECK(smem <= 200 * 1024, "fp32 attention: %d tokens need %zu bytes of shared memory", N, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static char tag;
+  if (first_use_on_device(&tag))  // the largest size this path accepts: set once per device
+    DAV2_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   dim3 grid((unsigned)((N + 3) / 4), (unsigned)(D / 64), (unsigned)B);
   ProfScope ps(PC_OTHER, 4.0 * B * (D / 64) * (double)N * N * 64.0, 0.0, stream);
   attention_f32_kernel<<<grid, 128, smem, stream>>>(qkv, out, N, D);

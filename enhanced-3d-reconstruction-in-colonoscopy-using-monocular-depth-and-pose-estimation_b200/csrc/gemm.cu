@@ -23,11 +23,10 @@ int pick_bn(int N) {
 template <int BN, int MODE>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;  // per instantiation; attribute is per-function, per-device (single device per process)
-  if (!configured) {
+  static char tag;  // per instantiation; the attribute is per function AND per device
+  if (first_use_on_device(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
-    configured = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   if (tiles <= 0) return 0;
@@ -66,11 +65,10 @@ int launch_gemm(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB
 template <int BN, int MODE>
 static int launch2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, gemm2_wide_epi(BN, MODE)>;
-  static bool configured = false;
-  if (!configured) {
+  static char tag;
+  if (first_use_on_device(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
-    configured = true;
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
@@ -111,12 +109,11 @@ static int env_flag(const char* name, int dflt) {
 template <int BN, int MODE>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<BN>;
-  static bool configured = false;
+  static char tag;
   static int bo_mode = 0;
-  if (!configured) {
+  if (first_use_on_device(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(conv_halo_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     bo_mode = env_flag("DAV2_HALO_BO", 0);
-    configured = true;
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
