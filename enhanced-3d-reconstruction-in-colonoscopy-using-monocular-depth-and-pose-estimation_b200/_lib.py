@@ -6,8 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# DAV2_LIB_PATH: A/B an alternative build of the same library (profiling scripts only)
-LIB_PATH = os.environ.get("DAV2_LIB_PATH") or os.path.join(_HERE, "libdav2_b200.so")
+# The product always loads the in-tree build.  (Profiling scripts that A/B another build of the same library assign
+# ``_lib.LIB_PATH`` themselves before the first ``load()``; no environment variable can swap the library.)
+LIB_PATH = os.path.join(_HERE, "libdav2_b200.so")
 
 c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -35,6 +36,7 @@ SIGNATURES = {
     "dav2_weights_complete": (c_int, [c_void_p]),
     "dav2_set_pos_embed": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dav2_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dav2_set_capture_logits": (c_int, [c_void_p, c_int]),
     "dav2_debug_buffer": (c_int, [c_void_p, C.c_char_p, C.POINTER(c_void_p), C.POINTER(c_i64)]),
     "dav2_debug_read": (c_int, [c_void_p, C.c_char_p, c_void_p, c_i64, c_void_p]),
     "dav2_resize_depth": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

@@ -71,6 +71,13 @@ int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W,
   return m->impl.forward(x, B, H, W, depth, S(stream));
 }
 
+int dav2_set_capture_logits(dav2_model* m, int32_t on) {
+  DAV2_CHECK(m, "null model");
+  DAV2_CHECK(m->impl.fmt != FMT_F32 || !on, "dav2_set_capture_logits: not available in the fp32 validation engine");
+  m->impl.capture_logits = on != 0;
+  return 0;
+}
+
 int dav2_debug_buffer(dav2_model* m, const char* name, void** ptr, int64_t* bytes) {
   DAV2_CHECK(m && name && ptr && bytes, "dav2_debug_buffer: null argument");
   return m->impl.debug_buffer(name, ptr, bytes);
@@ -214,8 +221,10 @@ int dav2_attention_h16(const void* qkv, void* out, int32_t B, int32_t N, int32_t
   if (int rc = require_sm100()) return rc;
   DAV2_CHECK(qkv && out, "dav2_attention_h16: null pointer");
   uint32_t lbo = 1024, sbo = 1024;
+#ifdef DAV2_PROFILING_KNOBS  // descriptor-stride experiments; never compiled into the shipped library
   if (const char* e = getenv("DAV2_ATT_VLBO")) lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("DAV2_ATT_VSBO")) sbo = (uint32_t)atoi(e);
+#endif
   return launch_attention((const h16*)qkv, (h16*)out, B, N, D, fmt, S(stream), lbo, sbo);
 }
 

@@ -384,24 +384,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cudaStream_t stream, uint32_t v_lbo,
                      uint32_t v_sbo) {
   DAV2_CHECK(D % 64 == 0 && N > 0 && B > 0, "attention: bad shape B=%d N=%d D=%d", B, N, D);
-  // DAV2_ATTN_EMU: pairs out of every 8 whose 2^x is emulated on the FMA pipe; DAV2_ATTN_KV: keys per tile (128 or 64).
-  // Both were tuned on B200; the environment overrides exist for profiling only.
-  static int emu = -1, kv = 64;
+  // emu: pairs out of every 8 whose 2^x is emulated on the FMA pipe; kv: keys per tile (128 or 64).  Both were tuned on
+  // B200.  The environment overrides exist in profiling builds only (-DDAV2_PROFILING_KNOBS).
+  int emu = 2, kv = 64;
   constexpr int SMEM128 = ATT_TILE + 4 * 128 * 128 + 128, SMEM64 = ATT_TILE + 4 * 64 * 128 + 128;
+#ifdef DAV2_PROFILING_KNOBS
+  if (const char* e = getenv("DAV2_ATTN_EMU")) emu = atoi(e);
+  DAV2_CHECK(emu == 0 || emu == 2 || emu == 3, "DAV2_ATTN_EMU must be 0, 2 or 3");
+  if (const char* k = getenv("DAV2_ATTN_KV")) kv = atoi(k);
+  DAV2_CHECK(kv == 64 || kv == 128, "DAV2_ATTN_KV must be 64 or 128");
+#endif
   static char tag;
-  if (first_use_on_device(&tag)) {
-    const char* e = getenv("DAV2_ATTN_EMU");
-    emu = e ? atoi(e) : 2;
-    DAV2_CHECK(emu == 0 || emu == 2 || emu == 3, "DAV2_ATTN_EMU must be 0, 2 or 3");
-    const char* k = getenv("DAV2_ATTN_KV");
-    kv = k ? atoi(k) : 64;
-    DAV2_CHECK(kv == 64 || kv == 128, "DAV2_ATTN_KV must be 64 or 128");
+  if (!device_setup_done(&tag)) {  // registered only after every attribute call succeeded: a failure is retried
 #define DAV2_ATTN_CFG(F, E)                                                                                                  \
   DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128));     \
   DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64))
     DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3);
     DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3);
 #undef DAV2_ATTN_CFG
+    device_setup_mark(&tag);
   }
   CUtensorMap tm, tmkv;
   if (int rc = make_tmap_2d(&tm, qkv, (uint64_t)B * N, (uint64_t)3 * D, (uint64_t)3 * D, 128)) return rc;

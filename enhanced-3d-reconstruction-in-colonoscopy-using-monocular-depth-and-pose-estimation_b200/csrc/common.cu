@@ -79,15 +79,23 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
   return 0;
 }
 
-// cudaFuncSetAttribute is per (function, device): `first_use_on_device(tag)` is true exactly once per device and tag
-// (tag = the address of a function-local static), also when several devices are driven from one process.
-bool first_use_on_device(const void* tag) {
-  static std::mutex mu;
-  static std::set<std::pair<int, const void*>> seen;
+// cudaFuncSetAttribute is per (function, device).  `device_setup_done(tag)` says whether the set-up keyed by `tag` (the
+// address of a function-local static) has SUCCEEDED on the current device; the caller runs the set-up, returning early
+// on any error, and only then calls `device_setup_mark(tag)` -- a failed set-up is therefore retried by the next call
+// instead of being skipped for ever.  Works when several devices are driven from one process.
+static std::mutex g_setup_mu;
+static std::set<std::pair<int, const void*>> g_setup_seen;
+bool device_setup_done(const void* tag) {
   int dev = 0;
   cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lock(mu);
-  return seen.insert(std::make_pair(dev, tag)).second;
+  std::lock_guard<std::mutex> lock(g_setup_mu);
+  return g_setup_seen.count(std::make_pair(dev, tag)) != 0;
+}
+void device_setup_mark(const void* tag) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_setup_mu);
+  g_setup_seen.insert(std::make_pair(dev, tag));
 }
 
 int sm_count() {

@@ -329,7 +329,8 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
                    uint32_t tw, uint32_t th);
 
 int sm_count();
-bool first_use_on_device(const void* tag);  // true once per (device, tag): per-device kernel attribute set-up
+bool device_setup_done(const void* tag);   // per-(device, tag) kernel attribute set-up: done?  (common.cu)
+void device_setup_mark(const void* tag);   // ... call after the set-up succeeded
 
 }  // namespace dav2
 

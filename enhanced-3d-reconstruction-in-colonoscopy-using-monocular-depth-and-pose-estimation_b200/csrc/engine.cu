@@ -87,6 +87,7 @@ Model::Model(const dav2_config& c) : cfg(c) {
   heads = c.num_heads;
   F = c.features;
   fmt = c.precision == 2 ? FMT_F32 : (c.precision == 1 ? FMT_BF16 : FMT_F16);
+  cudaGetDevice(&device);
   blk.resize(L);
   memset(blk.data(), 0, sizeof(BlockW) * L);
   memset(proj_w, 0, sizeof(proj_w)); memset(proj_b, 0, sizeof(proj_b));
@@ -389,6 +390,15 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   std::string missing;
   DAV2_CHECK(weights_complete(&missing), "forward: weight '%s' was never loaded", missing.c_str());
   DAV2_CHECK(x && depth && B > 0, "forward: null pointer or empty batch");
+  {
+    int cur = -1;
+    DAV2_CUDA_OK(cudaGetDevice(&cur));
+    cudaPointerAttributes pa;
+    DAV2_CUDA_OK(cudaPointerGetAttributes(&pa, x));
+    DAV2_CHECK(cur == device && (pa.type != cudaMemoryTypeDevice || pa.device == device),
+               "forward: this handle lives on device %d but the call runs on device %d with x on device %d "
+               "(create one handle per device)", device, cur, pa.device);
+  }
   DAV2_CHECK(H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0, "forward: H=%d W=%d must be positive multiples of 14", H, W);
   if (fmt == FMT_F32) return forward_fp32(x, B, H, W, depth, stream);
   const int ph = H / 14, pw = W / 14, P = ph * pw, N = P + 1;
@@ -566,6 +576,7 @@ int Model::forward(const float* x, int B, int H, int W, float* depth, cudaStream
   {
     GemmParams p = blank_params(fmt);
     p.out = depth; p.bias = oc2_b; p.head_w = oc3_w; p.head_b = oc3_b; p.max_depth = cfg.max_depth;
+    if (capture_logits) RC(buf("logits", (size_t)B * H * W * 4, (void**)&p.out_logit));
     RC(conv3x3(GM_CONV_HEAD, O1U, B, H, W, F / 2, oc2_w, 32, p, stream));
   }
   return 0;

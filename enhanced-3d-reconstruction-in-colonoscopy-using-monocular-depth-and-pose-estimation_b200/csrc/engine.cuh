@@ -31,6 +31,7 @@ struct DevBuf {
 struct Model {
   dav2_config cfg;
   int D, L, heads, F;
+  int device = 0;  // the CUDA device the handle (weights + workspace) lives on; forward() refuses any other
   int fmt;  // FMT_F16 (default; the reference's AMP precision), FMT_BF16, or FMT_F32 (fp32 validation engine)
   // encoder
   h16* patch_w = nullptr;
@@ -46,6 +47,8 @@ struct Model {
   h16 *oc1_w = nullptr, *oc2_w = nullptr;
   float *oc1_b = nullptr, *oc2_b = nullptr, *oc3_w = nullptr;
   float oc3_b = 0.f;
+
+  bool capture_logits = false;  // dav2_set_capture_logits: keep the pre-sigmoid logits of the next forwards in buffer "logits"
 
   std::set<std::string> required, loaded;
   std::map<std::pair<int, int>, float*> pos_tables;

@@ -216,8 +216,10 @@ static int attention_f32(const float* qkv, float* out, int B, int N, int D, cuda
   const size_t smem = (size_t)4 * Npad * sizeof(float);
   DAV2_CHECK(smem <= 200 * 1024, "fp32 attention: %d tokens need %zu bytes of shared memory", N, smem);
   static char tag;
-  if (first_use_on_device(&tag))  // the largest size this path accepts: set once per device
+  if (!device_setup_done(&tag)) {  // the largest size this path accepts: set once per device
     DAV2_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    device_setup_mark(&tag);
+  }
   dim3 grid((unsigned)((N + 3) / 4), (unsigned)(D / 64), (unsigned)B);
   ProfScope ps(PC_OTHER, 4.0 * B * (D / 64) * (double)N * N * 64.0, 0.0, stream);
   attention_f32_kernel<<<grid, 128, smem, stream>>>(qkv, out, N, D);

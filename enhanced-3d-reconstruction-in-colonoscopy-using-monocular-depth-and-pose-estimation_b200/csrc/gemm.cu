@@ -24,9 +24,10 @@ template <int BN, int MODE>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static char tag;  // per instantiation; the attribute is per function AND per device
-  if (first_use_on_device(&tag)) {
+  if (!device_setup_done(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
+    device_setup_mark(&tag);
   }
   const int tiles = p.tiles_m * p.tiles_n;
   if (tiles <= 0) return 0;
@@ -66,9 +67,10 @@ template <int BN, int MODE>
 static int launch2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, gemm2_wide_epi(BN, MODE)>;
   static char tag;
-  if (first_use_on_device(&tag)) {
+  if (!device_setup_done(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
+    device_setup_mark(&tag);
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
@@ -101,19 +103,24 @@ int launch_gemm2(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap& tm
   return -3;
 }
 
+#ifdef DAV2_PROFILING_KNOBS
 static int env_flag(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+#endif
 
 template <int BN, int MODE>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<BN>;
   static char tag;
-  static int bo_mode = 0;
-  if (first_use_on_device(&tag)) {
+  int bo_mode = 0;
+#ifdef DAV2_PROFILING_KNOBS
+  bo_mode = env_flag("DAV2_HALO_BO", 0);
+#endif
+  if (!device_setup_done(&tag)) {
     DAV2_CUDA_OK(cudaFuncSetAttribute(conv_halo_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    bo_mode = env_flag("DAV2_HALO_BO", 0);
+    device_setup_mark(&tag);
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
@@ -133,21 +140,25 @@ int launch_conv_halo(int bn, int mode, const CUtensorMap& tmA, const CUtensorMap
   return -3;
 }
 
+// Kernel selection is a pure function of the shape in the shipped library; profiling builds (-DDAV2_PROFILING_KNOBS) can
+// force the per-tap / 1-CTA kernels with DAV2_CONV_HALO=0 / DAV2_GEMM2=0 for A/B measurements.
+static bool knob_on(const char* name) {
+#ifdef DAV2_PROFILING_KNOBS
+  return env_flag(name, 1) == 1;
+#else
+  (void)name;
+  return true;
+#endif
+}
+
 bool conv_halo_eligible(int bn, int mode, int tiles_m) {
-  static int on = -1;  // DAV2_CONV_HALO=0 falls back to the per-tap box loads
-  if (on < 0) on = env_flag("DAV2_CONV_HALO", 1);
-  if (on != 1 || tiles_m < 2) return false;
-  if (mode == GM_CONV_HEAD) return bn == 32 && env_flag("DAV2_GEMM2", 1) == 1;
+  if (!knob_on("DAV2_CONV_HALO") || tiles_m < 2) return false;
+  if (mode == GM_CONV_HEAD) return bn == 32 && knob_on("DAV2_GEMM2");
   return mode == GM_CONV_BF16 && (bn == 128 || bn == 256) && gemm2_eligible(bn, mode, tiles_m);
 }
 
 bool gemm2_eligible(int bn, int mode, int tiles_m) {
-  static int force = -1;  // DAV2_GEMM2=0 disables, =1 (default) enables the 2-CTA kernel
-  if (force < 0) {
-    const char* e = getenv("DAV2_GEMM2");
-    force = (e && e[0] == '0') ? 0 : 1;
-  }
-  return force == 1 && mode != GM_CONV_HEAD && (bn == 128 || bn == 256) && tiles_m >= 2;
+  return knob_on("DAV2_GEMM2") && mode != GM_CONV_HEAD && (bn == 128 || bn == 256) && tiles_m >= 2;
 }
 
 }  // namespace dav2

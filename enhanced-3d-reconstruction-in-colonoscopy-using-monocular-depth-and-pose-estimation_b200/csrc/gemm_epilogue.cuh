@@ -42,6 +42,7 @@ struct GemmParams {
   int convt_s, convt_cout;
   const float* head_w;   // [32]
   float head_b, max_depth;
+  float* out_logit;      // GM_CONV_HEAD, optional: pre-sigmoid logits [B,H,W] (parity instrumentation)
 };
 
 static constexpr int STG_ROW_BYTES = 36 * 4;  // 32 fp32 + 16 B pad: conflict-free row writes and column-group reads
@@ -284,7 +285,9 @@ __device__ __forceinline__ void epi_tile_head(const GemmParams& p, uint32_t t_ro
     acc = fmaf(fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + j), 0.0f), __ldg(p.head_w + j), acc);
   if (y < p.H && x < p.W) {
     const float s = 1.0f / (1.0f + __expf(-acc));
-    reinterpret_cast<float*>(p.out)[((long long)g.cb_img * p.H + y) * p.W + x] = s * p.max_depth;
+    const long long idx = ((long long)g.cb_img * p.H + y) * p.W + x;
+    reinterpret_cast<float*>(p.out)[idx] = s * p.max_depth;
+    if (p.out_logit) p.out_logit[idx] = acc;  // launch-uniform
   }
 }
 

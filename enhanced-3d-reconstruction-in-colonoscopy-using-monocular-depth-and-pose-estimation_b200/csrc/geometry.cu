@@ -205,7 +205,9 @@ int launch_backproject_multi(const float* depth, int B, int H, int W, const doub
   const long long HW = (long long)H * W;
   DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
   BpDst dst;
-  bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  // the 4-pixel path assumes at most ONE row change inside a quad (backproject_quad): frames narrower than 4 pixels take
+  // the scalar path
+  bool vec = (HW % 4 == 0) && (W >= 4) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
   for (int p = 0; p < BP_MAX_DST; ++p) {
     const bool on = p < n_dst;
     dst.xyz[p] = on ? xyz[p] : nullptr;

@@ -166,7 +166,7 @@ static inline int grid_for(long long total, int per_block = 256, int waves = 16)
 }
 
 // ---------------------------------------------------------------------------------------------- model
-PoseModel::PoseModel(int precision) : fmt(precision == 1 ? FMT_BF16 : FMT_F16) {}
+PoseModel::PoseModel(int precision) : fmt(precision == 1 ? FMT_BF16 : FMT_F16) { cudaGetDevice(&device); }
 
 PoseModel::~PoseModel() {
   for (void* p : owned) cudaFree(p);
@@ -292,6 +292,11 @@ int PoseModel::add_relu(const h16* a, const h16* b, h16* out, long long n, cudaS
 
 int PoseModel::forward(const float* x, int B, int H, int W, float* out7, cudaStream_t stream) {
   DAV2_CHECK(x && out7 && B > 0 && H >= 32 && W >= 32, "pose forward: bad arguments");
+  {
+    int cur = -1;
+    DAV2_CUDA_OK(cudaGetDevice(&cur));
+    DAV2_CHECK(cur == device, "pose forward: this handle lives on device %d but the call runs on device %d", device, cur);
+  }
   for (const char* k : {"fc.weight", "fc.bias", "head.0.weight", "head.0.bias", "head.1.weight", "head.1.bias", "head.2.weight",
                         "head.2.bias"})
     DAV2_CHECK(f32.count(k), "pose forward: '%s' was never loaded", k);

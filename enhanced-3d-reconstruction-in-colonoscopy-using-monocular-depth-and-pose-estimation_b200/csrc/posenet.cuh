@@ -12,6 +12,7 @@ struct ConvW {
 
 struct PoseModel {
   int fmt;
+  int device = 0;  // the CUDA device the handle lives on
   std::map<std::string, ConvW> conv;
   std::map<std::string, float*> f32;
   std::vector<void*> owned;

@@ -10,6 +10,7 @@ the device.  ``PointCloud`` mimics the small part of ``o3d.geometry.PointCloud``
 """
 from __future__ import annotations
 
+import glob
 import os
 from dataclasses import dataclass
 from pathlib import Path
@@ -144,6 +145,23 @@ def point_cloud_from_depth(depth, color, intrinsics: PinholeCameraIntrinsic, tra
     return PointCloud(pts, cols)
 
 
+def point_clouds_from_depth_batch(depths: np.ndarray, colors: np.ndarray | None, k4s: np.ndarray, t12s: np.ndarray | None,
+                                  depth_scale: float = 1000.0, depth_trunc: float = 3.0, device="cuda") -> PointCloud:
+    """Batched core: depths [B,H,W], colours [B,H,W,3] u8 or None, k4s [B,4], t12s [B,12] or None -> ONE cloud holding the
+    frames' valid points in frame order (one dav2_backproject launch for the whole batch)."""
+    d = torch.as_tensor(np.ascontiguousarray(depths).astype(np.float32)).to(device)
+    K = torch.as_tensor(np.asarray(k4s, dtype=np.float64))
+    T = None if t12s is None else torch.as_tensor(np.asarray(t12s, dtype=np.float64))
+    xyz, valid, _ = ops.backproject(d, K, T, depth_scale, depth_trunc, want_counts=False)
+    keep = valid.bool().reshape(-1)
+    pts = xyz.reshape(-1, 3)[keep]
+    cols = None
+    if colors is not None:
+        c = torch.as_tensor(np.ascontiguousarray(colors)).to(device).reshape(-1, 3)
+        cols = c[keep].float() / 255.0
+    return PointCloud(pts, cols)
+
+
 def generate_point_cloud(depth_image_path: str, color_image_path: str, intrinsics_path: str, position_file: str,
                          rotation_file: str, frame_idx: int) -> PointCloud:
     """depth_to_pointcloud.py:178-241."""
@@ -189,12 +207,69 @@ def write_ply(path: str, cloud: PointCloud) -> None:
         f.write(rec.tobytes())
 
 
-def main(depth_image_paths: list, color_image_paths: list, output_dir: str) -> PointCloud:
-    """depth_to_pointcloud.py:316-371 without the Poisson mesh (out of scope)."""
+def input_output_files(args) -> tuple:
+    """depth_to_pointcloud.py:53-122: (rgb files, depth files, output dir) from the CLI namespace (``img_path``,
+    ``depth_path``, ``ds_type``, ``outdir``; ``outdir`` is filled in on ``args`` like the reference does).
+
+    Quirks kept: with a FILE ``img_path`` the single-image branch hangs off the ``depth_path`` test (so a ``.txt`` image list
+    with a non-``.txt`` depth path is replaced by ``[img_path]``); SimCol RGB frames are the ``Frames_*`` folders without
+    ``_OP``, depths come from ``Frames_*_OP/depth``; lists are sorted per SyntheticColon_{I,II,III} sub-set."""
+    rgb_filenames, depth_filenames = [], []
+    if os.path.isfile(args.img_path):
+        if args.img_path.endswith("txt"):
+            with open(args.img_path, "r", encoding="utf-8") as f:
+                rgb_filenames = f.read().splitlines()
+        if args.depth_path.endswith("txt"):
+            with open(args.depth_path, "r", encoding="utf-8") as f:
+                depth_filenames = f.read().splitlines()
+        else:
+            rgb_filenames = [args.img_path]
+            if args.outdir is None:
+                args.outdir = str(Path(args.img_path).parent)
+    elif args.ds_type == "simcol":
+        base_dir = Path(args.img_path)
+        for suffix in ("I", "II", "III"):
+            rgb = glob.glob(str(base_dir / f"SyntheticColon_{suffix}/Frames_*/FrameBuffer_*.png"), recursive=True)
+            rgb_filenames.extend(sorted(p for p in rgb if "_OP" not in str(p)))
+            depth_filenames.extend(sorted(glob.glob(str(base_dir / f"SyntheticColon_{suffix}/Frames_*_OP/depth/Depth_*.png"),
+                                                    recursive=True)))
+        if args.outdir is None:
+            args.outdir = str(base_dir)
+    elif args.ds_type == "testing":
+        base_dir = Path(args.img_path)
+        rgb_filenames.extend(sorted(glob.glob(str(base_dir / "frame_*.jpg"), recursive=True)))
+        if args.outdir is None:
+            args.outdir = str(base_dir)
+    return rgb_filenames, depth_filenames, args.outdir
+
+
+def main(depth_image_paths: list, color_image_paths: list, output_dir: str, batch: int = 32) -> PointCloud:
+    """depth_to_pointcloud.py:316-371 without the Poisson mesh (out of scope).  Frames are read ``batch`` at a time and
+    every run of same-shaped frames is back-projected by ONE launch (per-frame intrinsics and poses are kernel inputs);
+    the reference builds one Open3D cloud per frame."""
+    import cv2
+
     combined = PointCloud()
-    for frame_idx, (dp, cp) in enumerate(zip(depth_image_paths, color_image_paths)):
-        cam, pos, rot = get_procedure_files(cp)
-        combined += generate_point_cloud(dp, cp, cam, pos, rot, frame_idx)
+    pairs = list(zip(depth_image_paths, color_image_paths))
+    for s in range(0, len(pairs), batch):
+        depths, colors, k4s, t12s = [], [], [], []
+        for frame_idx, (dp, cp) in enumerate(pairs[s:s + batch], start=s):
+            cam, pos, rot = get_procedure_files(cp)
+            depth_image = cv2.imread(dp, cv2.IMREAD_UNCHANGED)
+            color_image = cv2.imread(cp)
+            width, height = color_image.shape[:2]  # sic (generate_point_cloud)
+            depths.append(cv2.resize(depth_image, (width, height), interpolation=cv2.INTER_NEAREST))
+            colors.append(color_image)
+            k4s.append(load_camera_intrinsics(cam, width, height).k4())
+            t12s.append(load_transformation(pos, rot, frame_idx)[:3, :4].reshape(12))
+        i = 0
+        while i < len(depths):  # runs of equal shape -> one launch each
+            j = i + 1
+            while j < len(depths) and depths[j].shape == depths[i].shape and colors[j].shape == colors[i].shape:
+                j += 1
+            combined += point_clouds_from_depth_batch(np.stack(depths[i:j]), np.stack(colors[i:j]), np.asarray(k4s[i:j]),
+                                                      np.asarray(t12s[i:j]))
+            i = j
     combined = combined.voxel_down_sample(voxel_size=0.01)  # :357-359
     os.makedirs(output_dir, exist_ok=True)
     write_ply(f"{output_dir}/combined_point_cloud.ply", combined)

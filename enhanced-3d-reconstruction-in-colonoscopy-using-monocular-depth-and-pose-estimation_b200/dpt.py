@@ -115,6 +115,7 @@ class DepthAnythingV2(nn.Module):
         self.depth_head = _head_params(D, features, list(out_channels))
         self._cfg = (D, depth, heads, int(features), [int(c) for c in out_channels])
         self._handle = None
+        self._handle_device = None
         self._dirty = True
         self._pos_grids = set()
 
@@ -135,6 +136,7 @@ class DepthAnythingV2(nn.Module):
         if self._handle is not None:
             _lib.load().dav2_destroy(self._handle)
             self._handle = None
+        self._handle_device = None
         self._pos_grids = set()
 
     def __del__(self):
@@ -144,7 +146,13 @@ class DepthAnythingV2(nn.Module):
             pass
 
     def _ensure_engine(self, device):
-        if self._handle is not None and not self._dirty:
+        """One engine (packed weights + workspace) on ONE device, used from one stream at a time (include/dav2_b200.h:
+        "one handle per (device, host thread)").  An input on another GPU re-packs the engine there instead of launching
+        against the first device's weights."""
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._handle is not None and not self._dirty and self._handle_device == device:
             return
         lib = _lib.load()
         self._release()
@@ -161,6 +169,9 @@ class DepthAnythingV2(nn.Module):
                 check(lib.dav2_set_weight(h, k.encode(), t.data_ptr(), shape, t.dim()), f"dav2_set_weight({k})")
             if not lib.dav2_weights_complete(h):
                 raise Dav2Error("weights incomplete: " + lib.dav2_last_error().decode())
+            if getattr(self, "_capture_logits", False):
+                check(lib.dav2_set_capture_logits(h, 1), "dav2_set_capture_logits")
+        self._handle_device = device
         self._dirty = False
 
     def _pos_table(self, ph: int, pw: int) -> torch.Tensor:
@@ -200,6 +211,12 @@ class DepthAnythingV2(nn.Module):
             check(lib.dav2_forward(self._handle, x.data_ptr(), B, H, W, depth.data_ptr(),
                                    _lib.current_stream_ptr(x.device)), "dav2_forward")
         return depth
+
+    def capture_logits(self, on: bool = True) -> None:
+        """Parity instrumentation: keep the pre-sigmoid logits of the following forwards (``debug_buffer("logits", ...)``)."""
+        self._capture_logits = bool(on)
+        if self._handle is not None:
+            check(_lib.load().dav2_set_capture_logits(self._handle, 1 if on else 0), "dav2_set_capture_logits")
 
     def debug_buffer(self, name: str, dtype, shape) -> torch.Tensor:
         """Copy of an internal activation of the last forward (parity tests)."""

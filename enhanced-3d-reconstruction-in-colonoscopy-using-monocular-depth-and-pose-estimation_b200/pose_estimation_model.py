@@ -38,6 +38,7 @@ class PoseEstimationNet(nn.Module):
                                        nn.Linear(128, 64), nn.ReLU(), nn.Dropout(0.1), nn.Linear(64, 7))
         self.precision = precision
         self._handle = None
+        self._handle_device = None
         self._dirty = True
 
     def _apply(self, fn, *a, **k):
@@ -59,7 +60,11 @@ class PoseEstimationNet(nn.Module):
             pass
 
     def _ensure_engine(self, device):
-        if self._handle is not None and not self._dirty:
+        # one engine on ONE device, one stream at a time (include/dav2_b200.h); an input on another GPU re-packs it there
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._handle is not None and not self._dirty and self._handle_device == device:
             return
         lib = _lib.load()
         if self._handle is not None:
@@ -90,6 +95,7 @@ class PoseEstimationNet(nn.Module):
             put("fc.weight", bb.fc.weight); put("fc.bias", bb.fc.bias)
             for n, idx in enumerate((2, 5, 8)):
                 put(f"head.{n}.weight", self.pose_head[idx].weight); put(f"head.{n}.bias", self.pose_head[idx].bias)
+        self._handle_device = device
         self._dirty = False
 
     @torch.no_grad()

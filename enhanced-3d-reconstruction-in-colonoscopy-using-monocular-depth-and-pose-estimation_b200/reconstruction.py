@@ -23,6 +23,15 @@ def calculate_scale_factor(pred_rel_poses: torch.Tensor, gt_rel_poses: torch.Ten
     return torch.sum(pt * gt) / torch.sum(pt * pt)
 
 
+def pair_counts(total: int, world: int) -> list:
+    """Pairs (i, i+1) owned by each rank = the rank's frames except the video's last one; 0 for an empty shard."""
+    out = []
+    for r in range(world):
+        a, b = sharding.frame_range(total, r, world)
+        out.append(max(min(b, total - 1) - a, 0))
+    return out
+
+
 @torch.no_grad()
 def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float | torch.Tensor = 1.0,
                 batch: int = 16, depth_for_pose_scale: float = 1.0, initial_pose: Optional[torch.Tensor] = None,
@@ -35,7 +44,10 @@ def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float 
     a, b = sharding.frame_range(N, rank, world)
     hi = min(b + 1, N)  # halo frame for the last local pair
     dev = next(depth_model.parameters()).device
-    depth = torch.empty(hi - a, H, W, dtype=torch.float32, device=dev)
+    if b <= a:
+        # empty shard (N < world): no kernel runs here, but the rank still takes part in the pose all-gather below
+        hi = a
+    depth = torch.empty(max(hi - a, 0), H, W, dtype=torch.float32, device=dev)
     for s in range(a, hi, batch):
         e = min(s + batch, hi)
         depth[s - a:e - a] = depth_model(frames[s:e].to(dev))
@@ -51,7 +63,7 @@ def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float 
     # trajectory: gather the (tiny) relative poses, compose redundantly on every rank
     if world > 1:
         import torch.distributed as dist
-        counts = [max(min(sharding.frame_range(N, r, world)[1], N - 1) - sharding.frame_range(N, r, world)[0], 0) for r in range(world)]
+        counts = pair_counts(N, world)
         parts = [torch.zeros(c, 7, dtype=torch.float32, device=dev) for c in counts]
         dist.all_gather(parts, rel_local, group=group) if len(set(counts)) == 1 else _all_gather_ragged(parts, rel_local, rank, group)
         rel = torch.cat(parts)
@@ -60,7 +72,12 @@ def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float 
     rel = rel.clone()
     rel[:, :3] *= scale  # the network predicts unit translation directions (data_processing/pose_estimation.py:256-258)
     abs7, T12 = ops.compose_poses(rel.contiguous(), initial_pose, want_T12=True)
-    xyz, valid, counts_v = ops.backproject(depth[:b - a].contiguous(), k4, T12[a:b].contiguous())
+    if b > a:
+        xyz, valid, counts_v = ops.backproject(depth[:b - a].contiguous(), k4, T12[a:b].contiguous())
+    else:
+        xyz = torch.empty(0, H * W, 3, dtype=torch.float32, device=dev)
+        valid = torch.empty(0, H * W, dtype=torch.uint8, device=dev)
+        counts_v = torch.empty(0, dtype=torch.int32, device=dev)
     return {"depth": depth[:b - a], "rel": rel, "abs": abs7, "T12": T12, "xyz": xyz, "valid": valid, "counts": counts_v,
             "frame_range": (a, b)}
 

@@ -1,9 +1,10 @@
 """Frame-loop semantics of the reference's ``run.py:195-262`` on top of the B200 engine, with the output writers
 of ``run.py:239-262`` (raw ``.npy`` depth, min-max normalised 8-bit PNG, optional side-by-side with the input).
 
-Differences by design: frames are processed in BATCHES (the reference runs batch 1 with one sync per frame);
-the Spectral colour map needs matplotlib, which the reference imports but this image lacks, so colour output
-falls back to grayscale unless matplotlib is importable."""
+Differences by design: frames are processed in BATCHES (the reference runs batch 1 with one sync per frame).
+The colour output uses matplotlib's ``Spectral`` map exactly as ``run.py:160,245-248`` does; matplotlib is not in
+this image, so its 256-entry lookup table is rebuilt here from the 11 ColorBrewer anchors with matplotlib's own
+``LinearSegmentedColormap`` arithmetic (``spectral_lut``) -- colour PNGs never silently degrade to grayscale."""
 from __future__ import annotations
 
 import os
@@ -21,16 +22,34 @@ def depth_to_uint8(depth: np.ndarray) -> np.ndarray:
     return d.astype(np.uint8)
 
 
+# ColorBrewer 11-class "Spectral" anchors = matplotlib._cm._Spectral_data (8-bit values / 255)
+_SPECTRAL_ANCHORS = np.array([(158, 1, 66), (213, 62, 79), (244, 109, 67), (253, 174, 97), (254, 224, 139), (255, 255, 191),
+                              (230, 245, 152), (171, 221, 164), (102, 194, 165), (50, 136, 189), (94, 79, 162)],
+                             dtype=np.float64) / 255.0
+_SPECTRAL_LUT = None
+
+
+def spectral_lut() -> np.ndarray:
+    """matplotlib.colormaps.get_cmap("Spectral") as its [256,3] float64 lookup table (run.py:160): piecewise-linear through the
+    anchors at x = linspace(0,1,11), sampled at linspace(0,1,256) the way matplotlib.colors._create_lookup_table does."""
+    global _SPECTRAL_LUT
+    if _SPECTRAL_LUT is None:
+        x = np.linspace(0.0, 1.0, len(_SPECTRAL_ANCHORS))
+        xind = np.linspace(0.0, 1.0, 256)
+        ind = np.searchsorted(x, xind)[1:-1]
+        dist = (xind[1:-1] - x[ind - 1]) / (x[ind] - x[ind - 1])
+        y = _SPECTRAL_ANCHORS
+        mid = dist[:, None] * (y[ind] - y[ind - 1]) + y[ind - 1]
+        _SPECTRAL_LUT = np.clip(np.concatenate([y[:1], mid, y[-1:]]), 0.0, 1.0)
+    return _SPECTRAL_LUT
+
+
 def colorize(depth_u8: np.ndarray, grayscale: bool) -> np.ndarray:
-    """run.py:245-248: grayscale x3, or matplotlib 'Spectral_r' -> BGR."""
-    if not grayscale:
-        try:
-            import matplotlib
-            cmap = matplotlib.colormaps.get_cmap("Spectral_r")
-            return (cmap(depth_u8)[:, :, :3] * 255)[:, :, ::-1].astype(np.uint8)
-        except ImportError:
-            pass
-    return np.repeat(depth_u8[..., np.newaxis], 3, axis=-1)
+    """run.py:245-248: grayscale x3, or ``(cmap(depth)[:, :, :3] * 255)[:, :, ::-1].astype(uint8)`` with cmap = matplotlib
+    'Spectral' (an integer image indexes the colour table directly) -> BGR."""
+    if grayscale:
+        return np.repeat(depth_u8[..., np.newaxis], 3, axis=-1)
+    return (spectral_lut()[depth_u8] * 255)[:, :, ::-1].astype(np.uint8)
 
 
 def output_path(filename: str, outdir: str) -> str:

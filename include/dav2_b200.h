@@ -14,7 +14,9 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
  *     no call synchronises except dav2_create / dav2_set_weight (host-side packing + H2D copy);
  *   - return 0 on success, <0 on error; dav2_last_error() returns a thread-local message;
- *   - one handle per (device, host thread); a handle is not thread-safe;
+ *   - one handle per (device, host thread); a handle is not thread-safe, and its workspace is shared by all of its
+ *     calls: issue the forwards of ONE handle on ONE stream at a time (two streams need two handles, or an event
+ *     between them); the handle must be used on the device it was created on (checked);
  *   - there is NO CPU fallback: without an sm_100 device every compute call fails.
  */
 #ifndef DAV2_B200_H
@@ -64,6 +66,11 @@ int dav2_set_pos_embed(dav2_model* m, int32_t ph, int32_t pw, const float* table
 /* DepthAnythingV2.forward(x[B,3,H,W]) -> depth[B,H,W]   (lightning_model.py:301, :358; external dpt.py)
  * x: device fp32 NCHW, already ImageNet-normalised; H, W multiples of 14.  depth: device fp32. */
 int dav2_forward(dav2_model* m, const float* x, int32_t B, int32_t H, int32_t W, float* depth, void* stream);
+
+/* Parity instrumentation (compare PRE-sigmoid logits, not only the saturating depth): when on, every
+ * following dav2_forward also keeps the head's pre-sigmoid logits as the fp32 [B,H,W] debug buffer "logits"
+ * (depth = max_depth * sigmoid(logit); external dpt.py DPTHead output_conv2).  Tensor-core engine only. */
+int dav2_set_capture_logits(dav2_model* m, int32_t on);
 
 /* Parity / debugging: look up an internal activation buffer of the LAST forward by name
  * ("tap0".."tap3" h16 [B*ph*pw, D]; "x" fp32 residual stream; "path1" ...).  Returns device ptr + bytes. */

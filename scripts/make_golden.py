@@ -10,6 +10,8 @@ Reference functions executed (unmodified, imported from /root/reference):
   scipy Rotation.from_quat(..).as_matrix()       as used by depth_to_pointcloud.py:168
 and the explicit back-projection block of depth_to_pointcloud_dav2.py:300-313 (inline code in
 ``main``; not importable as a function, so its six numpy lines are evaluated here on the fixture).
+``config1_fixture`` adds BASELINE configs[0]: the left 475x475 crop of the reference's FrameBuffer_0051.png (copied as a
+PNG fixture) through the oracle's infer_image and the same explicit block.
 """
 import os
 import sys
@@ -131,6 +133,46 @@ def pose_metric_fixtures():
                         qdist=np.array([ref.quaternion_distance(gt[0, 3:], pred[0, 3:])]))
 
 
+def config1_fixture():
+    """BASELINE configs[0]: left 475x475 crop of the reference's own FrameBuffer_0051.png ->
+    cv2.INTER_CUBIC to 518x518 -> infer_image(img, 518) (vits, seed-0 oracle weights) -> the explicit back-projection
+    block of depth_to_pointcloud_dav2.py:300-313 evaluated with K scaled to 518 (datasets/UnityCam/cam.txt:1).
+    Writes the crop (PNG) and a stride-7 sample of the oracle depth + the reference formula's points."""
+    import cv2
+    sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
+    from oracle import dav2_oracle as O
+    img = cv2.imread(os.path.join(REF, "FrameBuffer_0051.png"))
+    crop = np.ascontiguousarray(img[:, :475])
+    assert crop.shape == (475, 475, 3)
+    cv2.imwrite(os.path.join(OUT, "FrameBuffer_0051_left475.png"), crop)
+    img518 = cv2.resize(crop, (518, 518), interpolation=cv2.INTER_CUBIC)
+    torch.set_num_threads(8)
+    oracle = O.build_oracle("vits", seed=0)
+    depth = oracle.infer_image(img518, 518)
+    assert depth.shape == (518, 518) and depth.dtype == np.float32
+    cam = [float(v) for v in open(os.path.join(REF, "datasets/UnityCam/cam.txt")).readline().split(",")]
+    s = 518.0 / 475.0
+    fx, fy, cx, cy = cam[0] * s, cam[4] * s, cam[2] * s, cam[5] * s
+    width = height = 518
+    # --- depth_to_pointcloud_dav2.py:300-313, verbatim arithmetic -------------------------------------------------
+    x, y = np.meshgrid(np.arange(width), np.arange(height))
+    x = (x - cx) / fx
+    y = (y - cy) / fy
+    z = np.array(depth)
+    points = np.stack((np.multiply(x, z), np.multiply(y, z), z), axis=-1).reshape(-1, 3)
+    # ---------------------------------------------------------------------------------------------------------------
+    sub = np.zeros((518, 518), bool)
+    sub[::7, ::7] = True
+    np.savez_compressed(os.path.join(OUT, "config1_vits.npz"), k4=np.array([fx, fy, cx, cy]), stride=np.array(7),
+                        depth_sub=depth[::7, ::7], points_sub=points[sub.reshape(-1)],
+                        depth_stats=np.array([depth.min(), depth.max(), depth.mean(), depth.std()], dtype=np.float64))
+    print("config1:", depth.min(), depth.max(), depth.mean(), depth.std())
+
+
 if __name__ == "__main__":
-    main()
-    pose_metric_fixtures()
+    if len(sys.argv) > 1 and sys.argv[1] == "config1":
+        config1_fixture()
+    else:
+        main()
+        pose_metric_fixtures()
+        config1_fixture()

@@ -3,6 +3,9 @@ Usage: python scripts/prof_ops.py [gemm|conv|attn|all] [reps]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from dav2_b200 import _lib
+if os.environ.get("PROF_LIB"):  # A/B another build of the library (profiling only): set before the first load()
+    _lib.LIB_PATH = os.environ["PROF_LIB"]
 from dav2_b200 import ops
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -59,7 +62,7 @@ if what in ("attn", "all", "attntrace"):
         ms = e0.elapsed_time(e1) / 20
         print("attention EMU=%s: %.3f ms  %.0f TFLOP/s" % (os.environ.get("DAV2_ATTN_EMU", "default"), ms, 4 * 64 * 16 * 1370 * 1370 * 64 / ms / 1e9))
 if what == "attntrace":
-    # in-kernel timeline (library built with -DATTN_TRACE, selected through DAV2_LIB_PATH)
+    # in-kernel timeline (library built with -DATTN_TRACE, selected through PROF_LIB)
     import ctypes, numpy as np
     from dav2_b200 import _lib
     lib = _lib.load()

@@ -37,7 +37,8 @@ def test_backproject_golden_fixture(golden_dir):
     assert _rel_err_points(w[0].cpu().numpy()[v].astype(np.float64), g["world"][v]).max() < POINT_RTOL
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 1, 1), (2, 7, 5), (3, 37, 53), (2, 518, 518)])
+@pytest.mark.parametrize("B,H,W", [(1, 1, 1), (2, 7, 5), (3, 37, 53), (2, 518, 518),
+                                   (2, 4, 1), (1, 8, 2), (1, 4, 3), (1, 2, 6)])  # strips narrower than one 4-pixel quad
 def test_backproject_vs_oracle(B, H, W):
     from dav2_b200 import ops
     rng = np.random.default_rng(B * 1000 + H)
@@ -211,6 +212,20 @@ def test_point_cloud_api(tmp_path, golden_dir):
     assert len(both) == 2 * len(pc) and both.points.shape == (2 * len(pc), 3)
     d2p.write_ply(str(tmp_path / "c.ply"), both)
     assert os.path.getsize(tmp_path / "c.ply") > 27 * len(both)
+    # main (depth_to_pointcloud.py:316-371): frames batched into one back-projection launch == the per-frame clouds fused
+    depth1 = rng.integers(0, 4000, size=(H, W)).astype(np.uint16)
+    cv2.imwrite(str(root / "Frames_S1" / "Depth_0001.png"), depth1)
+    cv2.imwrite(str(root / "Frames_S1" / "FrameBuffer_0001.png"), color[::-1].copy())
+    dps = [str(root / "Frames_S1" / f"Depth_000{i}.png") for i in (0, 1)]
+    cps = [str(root / "Frames_S1" / f"FrameBuffer_000{i}.png") for i in (0, 1)]
+    fused = d2p.main(dps, cps, str(tmp_path / "out"))
+    per_frame = d2p.PointCloud()
+    for i in (0, 1):
+        per_frame += d2p.generate_point_cloud(dps[i], cps[i], cam, pos, rot, i)
+    want = per_frame.voxel_down_sample(0.01)
+    assert len(fused) == len(want) > 0
+    np.testing.assert_allclose(fused.points, want.points, rtol=1e-6, atol=1e-7)
+    assert os.path.exists(tmp_path / "out" / "combined_point_cloud.ply")
 
 
 @pytest.mark.parametrize("n,voxel,with_rgb,with_valid", [(1, 0.01, False, False), (1000, 0.05, True, False),

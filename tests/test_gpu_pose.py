@@ -20,7 +20,8 @@ def _build(seed=0, precision="fp16"):
     return ref, net.cuda().eval()
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 224, 224), (3, 98, 126)])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 224, 224), (3, 98, 126),
+                                   (2, 518, 518)])  # the frame size of BASELINE configs[3] (stacked 518^2 pairs)
 def test_pose_net_matches_oracle(B, H, W):
     ref, net = _build()
     g = torch.Generator().manual_seed(5)

@@ -53,6 +53,17 @@ def test_run_writers():
     u8 = run.depth_to_uint8(d)
     assert u8.dtype == np.uint8 and u8.min() == 0 and u8.max() == 255
     assert run.colorize(u8, grayscale=True).shape == (3, 4, 3)
+    # run.py:160,245-248: matplotlib "Spectral" (not reversed), integer image indexes the 256-entry table; BGR out.
+    # Known answers of matplotlib.colormaps["Spectral"]: entry 0 / 255 are the first / last ColorBrewer anchors,
+    # entry 128 = (0.99807766, 0.99923106, 0.74602076).
+    lut = run.spectral_lut()
+    assert lut.shape == (256, 3)
+    np.testing.assert_allclose(lut[0], np.array([158, 1, 66]) / 255.0, atol=1e-12)
+    np.testing.assert_allclose(lut[255], np.array([94, 79, 162]) / 255.0, atol=1e-12)
+    np.testing.assert_allclose(lut[128], [0.99807766, 0.99923106, 0.74602076], atol=1e-8)
+    col = run.colorize(np.array([[0, 255, 128]], dtype=np.uint8), grayscale=False)
+    assert col.dtype == np.uint8 and col[0, 0].tolist() == [66, 1, 158] and col[0, 1].tolist() == [162, 79, 94]
+    assert col[0, 2].tolist() == [190, 254, 254]
     assert run.output_path("/a/b/FrameBuffer_0051.png", "/out") == "/out/FrameBuffer_0051.png"
 
 
@@ -81,3 +92,37 @@ def test_run_frames_loop(tmp_path):
     img = cv2.imread(os.path.join(out, "frame_2.png"))
     assert img.shape == (50, 90 + 50 + 90, 3)
     assert run.run_frames(m, files, out, input_size=70) == []  # everything exists -> skipped
+
+
+def test_input_output_files(tmp_path):
+    """depth_to_pointcloud.py:53-122 on a SimCol-shaped tree, a 'testing' folder, list files and a single image."""
+    from types import SimpleNamespace as NS
+    from dav2_b200 import depth_to_pointcloud as d2p
+    base = tmp_path / "SyntheticColon"
+    for sub, frames in (("I", "Frames_S1"), ("II", "Frames_B2")):
+        (base / f"SyntheticColon_{sub}" / frames).mkdir(parents=True)
+        (base / f"SyntheticColon_{sub}" / f"{frames}_OP" / "depth").mkdir(parents=True)
+        for i in (1, 0):
+            (base / f"SyntheticColon_{sub}" / frames / f"FrameBuffer_{i:04d}.png").write_bytes(b"x")
+            (base / f"SyntheticColon_{sub}" / f"{frames}_OP" / "depth" / f"Depth_{i:04d}.png").write_bytes(b"x")
+        (base / f"SyntheticColon_{sub}" / f"{frames}_OP" / f"FrameBuffer_9999.png").write_bytes(b"x")  # "_OP" is filtered
+    a = NS(img_path=str(base), depth_path="", ds_type="simcol", outdir=None)
+    rgb, dep, out = d2p.input_output_files(a)
+    assert [os.path.basename(p) for p in rgb] == ["FrameBuffer_0000.png", "FrameBuffer_0001.png"] * 2
+    assert all("_OP" not in p for p in rgb) and "SyntheticColon_I/" in rgb[0] and "SyntheticColon_II/" in rgb[2]
+    assert [os.path.basename(p) for p in dep] == ["Depth_0000.png", "Depth_0001.png"] * 2
+    assert out == str(base) and a.outdir == str(base)
+    t = tmp_path / "testing"
+    t.mkdir()
+    for n in ("frame_2.jpg", "frame_1.jpg", "other.jpg"):
+        (t / n).write_bytes(b"x")
+    rgb, dep, out = d2p.input_output_files(NS(img_path=str(t), depth_path="", ds_type="testing", outdir="o"))
+    assert [os.path.basename(p) for p in rgb] == ["frame_1.jpg", "frame_2.jpg"] and dep == [] and out == "o"
+    (tmp_path / "rgb.txt").write_text("a.png\nb.png\n")
+    (tmp_path / "dep.txt").write_text("da.png\ndb.png\n")
+    rgb, dep, out = d2p.input_output_files(NS(img_path=str(tmp_path / "rgb.txt"), depth_path=str(tmp_path / "dep.txt"),
+                                              ds_type="simcol", outdir=None))
+    assert rgb == ["a.png", "b.png"] and dep == ["da.png", "db.png"] and out is None
+    single = str(t / "frame_1.jpg")
+    rgb, dep, out = d2p.input_output_files(NS(img_path=single, depth_path="d.png", ds_type="simcol", outdir=None))
+    assert rgb == [single] and dep == [] and out == str(t)

@@ -140,3 +140,30 @@ def test_pos_embed_interpolation_shapes():
         assert q.shape == (1, 1 + 37 * 78, 384)
         d = m(O.synthetic_frames(1, 70, 98))
         assert d.shape == (1, 70, 98) and torch.isfinite(d).all()
+
+
+def test_config1_fixture_pins_oracle_and_geometry(golden_dir):
+    """BASELINE configs[0] fixture (scripts/make_golden.py config1): the reference's own frame through the oracle's
+    infer_image reproduces the committed depth sample, and the geometry oracle reproduces the points that the verbatim
+    depth_to_pointcloud_dav2.py:300-313 arithmetic produced from that depth."""
+    import os
+    import cv2
+    import numpy as np
+    from oracle import geometry_oracle as geo
+    g = np.load(os.path.join(golden_dir, "config1_vits.npz"))
+    crop = cv2.imread(os.path.join(golden_dir, "FrameBuffer_0051_left475.png"))
+    assert crop is not None and crop.shape == (475, 475, 3)
+    img518 = cv2.resize(crop, (518, 518), interpolation=cv2.INTER_CUBIC)
+    oracle = O.build_oracle("vits", seed=0)
+    depth = oracle.infer_image(img518, 518)
+    s = int(g["stride"])
+    assert np.abs(depth[::s, ::s] - g["depth_sub"]).max() < 2e-3  # summation order differs with the thread count only
+    np.testing.assert_allclose([depth.min(), depth.max(), depth.mean(), depth.std()], g["depth_stats"], rtol=2e-3)
+    # K scaled from 475 to 518 (datasets/UnityCam/cam.txt:1) == SURVEY.md 8d config 1
+    np.testing.assert_allclose(g["k4"], [170.1677, 169.8526, 194.7248, 198.2624], atol=1e-3)
+    full = np.zeros((518, 518), np.float32)
+    full[::s, ::s] = g["depth_sub"]
+    pts, valid = geo.backproject(full, tuple(g["k4"]), np.eye(4))
+    sub = np.zeros((518, 518), bool)
+    sub[::s, ::s] = True
+    np.testing.assert_allclose(pts[sub.reshape(-1)], g["points_sub"], rtol=1e-12, atol=1e-15)

@@ -95,3 +95,16 @@ def test_cloud_gather_needs_the_library_and_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             sharding.CloudGather(2, 16, "cuda")
+
+
+def test_pair_counts_with_empty_shards():
+    """reconstruction.reconstruct: a rank whose shard is empty (fewer frames than ranks) owns no pair and runs no kernel,
+    but the per-rank pair counts every rank derives must still add up to N - 1."""
+    from dav2_b200 import reconstruction as rc
+    assert rc.pair_counts(10, 1) == [9]
+    assert rc.pair_counts(10, 4) == [3, 3, 2, 1]
+    assert rc.pair_counts(3, 8) == [1, 1, 0, 0, 0, 0, 0, 0]
+    assert rc.pair_counts(1, 2) == [0, 0] and rc.pair_counts(0, 2) == [0, 0]
+    for total in (0, 1, 2, 5, 1000):
+        for world in (1, 2, 3, 8):
+            assert sum(rc.pair_counts(total, world)) == max(total - 1, 0)
