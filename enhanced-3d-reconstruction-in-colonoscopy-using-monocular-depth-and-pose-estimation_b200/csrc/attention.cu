@@ -60,6 +60,28 @@ __device__ __forceinline__ float2 ex2_emu2(float2 x) {
   return o;
 }
 
+// Two round-2 experiments are kept as A/B builds (scripts/build_attn_variants.sh); both measured SLOWER than the default
+// on B200 (vitl shape, 64 x 16 heads x 1370 tokens, same box: default 0.675 ms):
+//   -DATTN_SPECULATIVE  no row max after the first tile: exponentiate against the first tile's max, the tile's row sum
+//                       (<= 2^13) is the overflow guard, recentre + recompute on the rare violation.  Removes 32 FMNMX3 +
+//                       vote per tile but keeps the S row live to the end of the tile (128 registers): 0.696 ms.
+//   -DATTN_PREFETCH     tcgen05.ld of S(j+1) issued before the P hand-over of tile j when it is already committed: 0.733 ms.
+// What they showed: the softmax warps are bound by their OWN instruction stream (ncu source page: 28 % fixed-latency
+// dependency stalls, 18 % issuing, only 12 % lost arbitration; XU 52 %, issue 56 %), not by the max -> vote chain or the
+// TMEM round trip.
+#if !defined(ATTN_SPECULATIVE) && !defined(ATTN_PREFETCH)  // S registers die inside the exp loop, none prefetched
+#define ATTN_REGS_WG0 40
+#define ATTN_REGS_WG1 120
+#else
+#define ATTN_REGS_WG0 32
+#define ATTN_REGS_WG1 128
+#endif
+#if ATTN_REGS_WG0 >= 40  // the unrolled issue loops keep ~10 descriptor registers live: they spill at 32
+#define ATTN_MMA_UNROLL _Pragma("unroll")
+#else
+#define ATTN_MMA_UNROLL _Pragma("unroll 1")
+#endif
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -73,6 +95,19 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
   return r;
+}
+
+// max of a row of S held in registers: eight independent FMNMX3 chains (a single running max is a 64-deep dependent chain)
+template <int KV>
+__device__ __forceinline__ float row_max(const uint32_t (&sreg)[KV]) {
+  float mxc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mxc[c] = fmaxf(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
+#pragma unroll
+  for (int i = 16; i < KV; i += 16)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mxc[c] = fmax3(mxc[c], __uint_as_float(sreg[i + 2 * c]), __uint_as_float(sreg[i + 2 * c + 1]));
+  return fmaxf(fmax3(mxc[0], mxc[1], mxc[2]), fmaxf(fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
 }
 
 // In-kernel timeline (profiling builds only, -DATTN_TRACE): clock64 stamps of one softmax lane and of the MMA issuer for
@@ -164,7 +199,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const uint32_t tS = tmem_base, tO = tmem_base + KV, tP = KV == 128 ? tmem_base + 192 : tmem_slot_ptr[1];
 
   if (warp < 4) {
-  setmaxnreg_dec<KV == 64 ? 40 : 48>();
+  setmaxnreg_dec<KV == 64 ? ATTN_REGS_WG0 : 48>();
   if (warp == 0) {
     // ---------------- TMA producer (whole warp, elected lane issues); tiles 0 and 1 were issued in the prologue ----
     for (int j = 2; j < p.nkv; ++j) {
@@ -192,7 +227,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     tc_fence_after();
     if (elect_one()) {
       const uint64_t kdesc = make_sw128_desc(sK, 16, 1024);
-#pragma unroll
+ATTN_MMA_UNROLL
       for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
       umma_commit(BAR_S_FULL);
       umma_commit(BAR_K_EMPTY);
@@ -209,7 +244,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tc_fence_after();
         if (elect_one()) {
           const uint64_t kdesc = make_sw128_desc(sK + s1 * KV_TILE, 16, 1024);
-#pragma unroll
+ATTN_MMA_UNROLL
           for (int k = 0; k < 4; ++k) umma_h16(tS, qdesc + 2u * k, kdesc + 2u * k, idesc_s, (uint32_t)(k != 0));
           umma_commit(BAR_S_FULL);
           umma_commit(BAR_K_EMPTY + 8 * s1);
@@ -222,7 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       ATTN_STAMP_M(11);
       tc_fence_after();
       if (elect_one()) {
-#pragma unroll
+ATTN_MMA_UNROLL
         for (int k = 0; k < KV / 16; ++k) {  // 16 keys per MMA = 8 TMEM columns of P
           const uint64_t vdesc = make_sw128_desc(sV + s * KV_TILE + k * 2048, p.v_lbo, p.v_sbo);
           umma_h16_ts(tO, tP + 8u * k, vdesc, idesc_o, (uint32_t)((j | k) != 0));  // O accumulates in TMEM across KV tiles
@@ -235,32 +270,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     }
   }
   } else {
-    setmaxnreg_inc<KV == 64 ? 120 : 208>();
+    setmaxnreg_inc<KV == 64 ? ATTN_REGS_WG1 : 208>();
     // ---------------- softmax / output (one query row per thread) ----------------
-    // The whole S row (128 fp32) is pulled into registers with ONE exposed TMEM round trip, which frees the
-    // S buffer at once (the issuer overlaps S(j+1) with this tile's softmax).  O accumulates in TMEM across
-    // KV tiles; it is rescaled (TMEM load-scale-store) only when some row's running max grew by more than
-    // 2^8 since its reference max was taken ("lazy rescaling": P <= 256 is harmless in fp16/bf16 with fp32
-    // accumulation, and the final O / l is independent of the reference).
+    // The whole S row (KV fp32) is pulled into registers with ONE exposed TMEM round trip, which frees the S buffer at
+    // once (the issuer overlaps S(j+1) with this tile's softmax).  O accumulates in TMEM across KV tiles; it is rescaled
+    // (TMEM load-scale-store) only when some row's running max grew by more than 2^8 since its reference max was taken
+    // ("lazy rescaling": P <= 256 is harmless in fp16/bf16 with fp32 accumulation, and the final O / l is independent of
+    // the reference).  Barrier "probes" are mbarrier.test_wait or absent: try_wait suspends the thread.
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float m_ref = -INFINITY, l = 0.f;
+    float m_ref = 0.f, l = 0.f;
     uint32_t sreg[KV];
-    uint32_t s_ready = mbar_try_wait(BAR_S_FULL, 0u);
+    bool prefetched = false;
 
     for (int j = 0; j < p.nkv; ++j) {
       const int nvalid = p.N - j * KV;  // keys of this tile inside the image (>= 1)
       ATTN_STAMP(0);
-      if (!s_ready) mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
-      ATTN_STAMP(1);
-      tc_fence_after();
+      if (!prefetched) {
+        mbar_wait(BAR_S_FULL, (uint32_t)j & 1u);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < KV / 32; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
-      // PV(j-1) done <=> O may be rescaled and the P columns rewritten.  The probe's ~100-cycle latency hides behind the
-      // TMEM load; only a miss falls into the blocking wait below.
-      uint32_t o_ready = (j == 0) ? 1u : mbar_try_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);
+        for (int c = 0; c < KV / 32; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+      }
+      ATTN_STAMP(1);
+      // PV(j-1) done <=> the P columns may be rewritten (and O rescaled on the slow path): waited for only where it is
+      // needed, right before the P store (an early try_wait "probe" here blocked the warp until PV(j-1) had finished)
+      uint32_t o_ready = (j == 0) ? 1u : 0u;
       tmem_ld_wait();
+#ifndef ATTN_NO_REGFENCE
+#pragma unroll
+      for (int i = 0; i < KV; ++i) asm volatile("" : "+r"(sreg[i]));  // consumers stay below the wait
+#endif
       ATTN_STAMP(2);
       tc_fence_before();
       mbar_arrive(BAR_S_EMPTY);  // S(j) is in registers: the issuer may overwrite the TMEM buffer with S(j+1)
@@ -269,61 +310,83 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         for (int i = 0; i < KV; ++i)
           if (i >= nvalid) sreg[i] = 0xff800000u;  // -inf
       }
-      // eight independent chains (a single running max is a 64-deep dependent chain: 'wait' stalls in ncu)
-      float mxc[8];
+      // O *= alpha (TMEM load-scale-store), l *= alpha, m_ref = m_new: needs PV(j-1) complete
+      auto rescale_to = [&](float m_new) {
+        const float alpha = fast_exp2((m_ref - m_new) * LOG2E);  // <= 1; exactly 1 for rows that did not move
+        if (!o_ready) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) has finished accumulating into O
+        o_ready = 1u;
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mxc[c] = fmaxf(__uint_as_float(sreg[2 * c]), __uint_as_float(sreg[2 * c + 1]));
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ov[16];
+          tmem_ld16(tO + lane_addr + c * 16, ov);
+          tmem_ld_wait();
 #pragma unroll
-      for (int i = 16; i < KV; i += 16)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mxc[c] = fmax3(mxc[c], __uint_as_float(sreg[i + 2 * c]), __uint_as_float(sreg[i + 2 * c + 1]));
-      const float mx = fmaxf(fmax3(mxc[0], mxc[1], mxc[2]), fmaxf(fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
-      ATTN_STAMP(3);
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const float m_new = fmaxf(m_ref, mx);
-        const bool need = (m_new - m_ref) * LOG2E > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          if (!o_ready) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) has finished accumulating into O
-          o_ready = 1u;
-          tc_fence_after();
-          const float alpha = need ? fast_exp2((m_ref - m_new) * LOG2E) : 1.0f;
-          if (need) m_ref = m_new;
-          l *= alpha;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t ov[16];
-            tmem_ld16(tO + lane_addr + c * 16, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st16(tO + lane_addr + c * 16, ov);
-          }
-          tmem_st_wait();
-          tc_fence_before();
+          for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st16(tO + lane_addr + c * 16, ov);
         }
-      }
-      ATTN_STAMP(4);
-      const float mscaled = m_ref * LOG2E;
-      const float2 l2e2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mscaled, -mscaled);
-      float2 rs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      uint32_t preg[KV / 2];
-#pragma unroll
-      for (int i = 0; i < KV / 2; ++i) {  // pair i = keys 2i, 2i+1
-        const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[2 * i]), __uint_as_float(sreg[2 * i + 1])), l2e2, nm2);
-        float2 e;
-        if ((i & 7) < EMU) {
-          e = ex2_emu2(x);
+        tmem_st_wait();
+        tc_fence_before();
+        l *= alpha;
+        m_ref = m_new;
+      };
+#ifndef ATTN_SPECULATIVE
+      {
+        const float mx = row_max<KV>(sreg);
+        if (j == 0) {
+          m_ref = mx;
         } else {
-          e.x = fast_exp2(x.x);
-          e.y = fast_exp2(x.y);
+          const float m_new = fmaxf(m_ref, mx);
+          const bool need = (m_new - m_ref) * LOG2E > 8.0f;  // lazy: P <= 2^8 is harmless
+          if (__any_sync(0xffffffffu, need)) rescale_to(need ? m_new : m_ref);
         }
-        rs[i & 3] = __fadd2_rn(rs[i & 3], e);
-        preg[i] = FP16 ? pack2<FMT_F16>(e.x, e.y) : pack2<FMT_BF16>(e.x, e.y);
       }
-      l += ((rs[0].x + rs[0].y) + (rs[1].x + rs[1].y)) + ((rs[2].x + rs[2].y) + (rs[3].x + rs[3].y));
+#else
+      if (j == 0) m_ref = row_max<KV>(sreg);
+#endif
+      ATTN_STAMP(3);
+      uint32_t preg[KV / 2];
+      float ts;
+#pragma unroll 1
+      for (int attempt = 0;; ++attempt) {
+        const float mscaled = m_ref * LOG2E;
+        const float2 l2e2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(-mscaled, -mscaled);
+        float2 rs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < KV / 2; ++i) {  // pair i = keys 2i, 2i+1
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[2 * i]), __uint_as_float(sreg[2 * i + 1])), l2e2, nm2);
+          float2 e;
+          if ((i & 7) < EMU) {
+            e = ex2_emu2(x);
+          } else {
+            e.x = fast_exp2(x.x);
+            e.y = fast_exp2(x.y);
+          }
+          rs[i & 3] = __fadd2_rn(rs[i & 3], e);
+          preg[i] = FP16 ? pack2<FMT_F16>(e.x, e.y) : pack2<FMT_BF16>(e.x, e.y);
+        }
+        ts = ((rs[0].x + rs[0].y) + (rs[1].x + rs[1].y)) + ((rs[2].x + rs[2].y) + (rs[3].x + rs[3].y));
+#ifndef ATTN_SPECULATIVE
+        break;
+#else
+        // !(ts <= 2^13) also catches inf / NaN sums.  The first tile (true max) and a recomputed tile have ts <= KV.
+        if (attempt != 0 || j == 0 || !__any_sync(0xffffffffu, !(ts <= 8192.0f))) break;
+        // ---- slow path (rare): recentre on the true maximum seen so far, rescale O and l, recompute the tile ----
+        rescale_to(fmaxf(m_ref, row_max<KV>(sreg)));
+#endif
+      }
+      l += ts;
       ATTN_STAMP(5);
+      // S(j+1) already committed?  Pull it into the (now dead) S registers before handing P over.
+      prefetched = false;
+#ifdef ATTN_PREFETCH
+      if (j + 1 < p.nkv && __all_sync(0xffffffffu, mbar_test_wait(BAR_S_FULL, (uint32_t)(j + 1) & 1u))) {
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < KV / 32; ++c) tmem_ld32(tS + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+        prefetched = true;
+      }
+#endif
       if (!o_ready) mbar_wait(BAR_O_FULL, (uint32_t)(j - 1) & 1u);  // PV(j-1) no longer reads the P columns
       tc_fence_after();
       ATTN_STAMP(6);
@@ -332,8 +395,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       // the in-kernel timeline), and the MMA no longer reads 32 KB of P per tile through shared memory.
 #pragma unroll
       for (int c = 0; c < KV / 64; ++c) tmem_st32(tP + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&preg[c * 32]));
-      // probe S(j+1) while the stores drain
-      s_ready = (j + 1 < p.nkv) ? mbar_try_wait(BAR_S_FULL, (uint32_t)(j + 1) & 1u) : 0u;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(BAR_P_FULL);
@@ -390,7 +451,7 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   constexpr int SMEM128 = ATT_TILE + 4 * 128 * 128 + 128, SMEM64 = ATT_TILE + 4 * 64 * 128 + 128;
 #ifdef DAV2_PROFILING_KNOBS
   if (const char* e = getenv("DAV2_ATTN_EMU")) emu = atoi(e);
-  DAV2_CHECK(emu == 0 || emu == 2 || emu == 3, "DAV2_ATTN_EMU must be 0, 2 or 3");
+  DAV2_CHECK(emu == 0 || emu == 2 || emu == 3 || emu == 4, "DAV2_ATTN_EMU must be 0, 2, 3 or 4");
   if (const char* k = getenv("DAV2_ATTN_KV")) kv = atoi(k);
   DAV2_CHECK(kv == 64 || kv == 128, "DAV2_ATTN_KV must be 64 or 128");
 #endif
@@ -399,8 +460,8 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
 #define DAV2_ATTN_CFG(F, E)                                                                                                  \
   DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128));     \
   DAV2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<F, E, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64))
-    DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3);
-    DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3);
+    DAV2_ATTN_CFG(true, 0); DAV2_ATTN_CFG(true, 2); DAV2_ATTN_CFG(true, 3); DAV2_ATTN_CFG(true, 4);
+    DAV2_ATTN_CFG(false, 0); DAV2_ATTN_CFG(false, 2); DAV2_ATTN_CFG(false, 3); DAV2_ATTN_CFG(false, 4);
 #undef DAV2_ATTN_CFG
     device_setup_mark(&tag);
   }
@@ -430,6 +491,7 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
   switch (emu) {
     case 0: DAV2_ATTN_GO(0); break;
     case 3: DAV2_ATTN_GO(3); break;
+    case 4: DAV2_ATTN_GO(4); break;
     default: DAV2_ATTN_GO(2); break;
   }
 #undef DAV2_ATTN_GO

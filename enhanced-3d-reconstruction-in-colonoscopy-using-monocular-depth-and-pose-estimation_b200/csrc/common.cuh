@@ -80,6 +80,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe.  mbarrier.try_wait may SUSPEND the thread (hardware sleep until the phase completes or a time limit
+// expires); a "probe" whose answer is only wanted if it is already there must be test_wait -- ncu showed a quarter of the
+// attention kernel's softmax-warp time blocked in try_wait probes that were meant to be free.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from . import evaluation, ops, sharding
-from .pose_estimation_model import stack_pairs
+from .pose_estimation_model import stack_pairs  # noqa: F401  (the windowed form below is the same stacking)
 
 
 def calculate_scale_factor(pred_rel_poses: torch.Tensor, gt_rel_poses: torch.Tensor) -> torch.Tensor:
@@ -48,18 +48,26 @@ def reconstruct(frames: torch.Tensor, depth_model, pose_model, k4, scale: float 
         # empty shard (N < world): no kernel runs here, but the rank still takes part in the pose all-gather below
         hi = a
     depth = torch.empty(max(hi - a, 0), H, W, dtype=torch.float32, device=dev)
-    for s in range(a, hi, batch):
-        e = min(s + batch, hi)
-        depth[s - a:e - a] = depth_model(frames[s:e].to(dev))
-    # relative poses of the local pairs (i, i+1), i in [a, min(b, N-1))
+    # relative poses of the local pairs (i, i+1), i in [a, min(b, N-1)): streamed batch by batch -- every batch of frames is
+    # uploaded once, its depth computed, and its pairs (plus the pair that straddles the previous batch) go through the
+    # pose network straight away, so neither the frames nor the [pairs, 8, H, W] stack is ever resident as a whole
     n_pairs = max(min(b, N - 1) - a, 0)
     rel_local = torch.zeros(n_pairs, 7, dtype=torch.float32, device=dev)
-    if n_pairs:
-        rgb = frames[a:a + n_pairs + 1].to(dev)
-        d = depth[:n_pairs + 1, None] * depth_for_pose_scale
-        pairs = stack_pairs(rgb, d)
-        for s in range(0, n_pairs, batch):
-            rel_local[s:s + batch] = pose_model(pairs[s:s + batch])
+    prev = None  # last (rgb, scaled depth) frame of the previous batch
+    for s in range(a, hi, batch):
+        e = min(s + batch, hi)
+        x = frames[s:e].to(dev, non_blocking=True)
+        d = depth_model(x)
+        depth[s - a:e - a] = d
+        f = torch.cat([x, d[:, None] * depth_for_pose_scale], dim=1)          # [n, 4, H, W]
+        first = s                                                              # global index of the first pair's frame i
+        if prev is not None:
+            f = torch.cat([prev, f], dim=0)
+            first = s - 1
+        if f.shape[0] > 1:
+            pairs = torch.cat([f[:-1], f[1:]], dim=1).contiguous()            # == stack_pairs on this window
+            rel_local[first - a:first - a + pairs.shape[0]] = pose_model(pairs)
+        prev = f[-1:]
     # trajectory: gather the (tiny) relative poses, compose redundantly on every rank
     if world > 1:
         import torch.distributed as dist

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+if os.environ.get("PROF_LIB"):  # A/B builds of the library under the SAME tests (profiling runs only; the product ignores it)
+    from dav2_b200 import _lib as _dav2_lib
+    _dav2_lib.LIB_PATH = os.environ["PROF_LIB"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -80,6 +80,43 @@ def test_attention(B, N, heads, dt):
     assert _relerr(out, ref) < 2 * TOL[dt]  # P is rounded to 16 bits before the PV product
 
 
+@pytest.mark.parametrize("dt", H16)
+@pytest.mark.parametrize("case", ["late_peak", "ramp", "early_peak", "huge", "tail_peak"])
+def test_attention_reference_max_slow_path(case, dt):
+    """The attention kernel keeps a REFERENCE max per row and rescales the TMEM accumulator lazily (only when a row's max
+    grew by more than 2^8); its -DATTN_SPECULATIVE build skips the per-tile max altogether and recentres when a tile's row
+    sum exceeds 2^13.  These score patterns force both slow paths: a key far above the earlier maxima late in the sequence,
+    scores ramping up tile after tile, the mirror image (later tiles underflow), scores in the hundreds, and a peak inside
+    the masked tail tile."""
+    from dav2_b200 import ops
+    B, N, heads = 2, 300, 2
+    D = heads * 64
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(B, N, heads, 64, generator=g) * 0.125
+    k = torch.randn(B, N, heads, 64, generator=g)
+    v = torch.randn(B, N, heads, 64, generator=g)
+    u = torch.randn(64, generator=g)
+    u = u / u.norm()
+    q = q + 1.0 * u  # every query has a component along u: adding c*u to a key adds ~c to its score
+    pos = torch.arange(N).view(1, N, 1, 1).float()
+    if case == "late_peak":
+        k[:, 200] += 30.0 * u          # score +30 (43 octaves) at key 200: tile 3 of 5
+    elif case == "ramp":
+        k = k + (pos / N) * 60.0 * u   # +12 per tile
+    elif case == "early_peak":
+        k[:, 3] += 40.0 * u            # the first tile holds the max: every later tile underflows
+    elif case == "huge":
+        k = k + (pos % 7 - 3) * 40.0 * u
+    else:
+        k[:, N - 1] += 50.0 * u        # last valid key of the (masked) tail tile
+    qkv = torch.cat([q.reshape(B * N, D), k.reshape(B * N, D), v.reshape(B * N, D)], dim=1).to(dt).cuda().contiguous()
+    out = ops.attention_h16(qkv, B, N, D)
+    qf, kf, vf = (t.reshape(B, N, heads, 64).transpose(1, 2).float() for t in qkv.split(D, dim=1))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2), dim=-1) @ vf).transpose(1, 2).reshape(B * N, D)
+    assert torch.isfinite(out.float()).all()
+    assert _relerr(out, ref) < 2 * TOL[dt]
+
+
 @pytest.mark.parametrize("rows,D", [(5, 384), (1370, 768), (2741, 1024)])
 @pytest.mark.parametrize("dt", H16)
 def test_layernorm(rows, D, dt):
