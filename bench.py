@@ -35,7 +35,7 @@ CONFIGS = {
             what="depth + compute_errors partial sums (test_step mask) + per-frame calculate_metrics partial sums"),
     3: dict(encoder="vitl", batch=64, size=518, scaling="weak",
             metric="frames/s DAv2-L 518^2 depth+pointcloud",
-            what="depth + pose chain + fused back-projection/SE(3)/validity + metric partial sums"),
+            what="depth + pose chain + ONE fused pass: back-projection/SE(3)/validity + metric partial sums"),
     4: dict(encoder="vitl", batch=64, size=518, scaling="strong", frames=1000,
             metric="frames/s DAv2-L 518^2 full reconstruction pass (depth + ResNet-18 pose + chain + world cloud)",
             what="reconstruction.reconstruct over a 1000-frame video: vitl depth, ResNet-18 pose on stacked pairs "
@@ -374,17 +374,17 @@ def main():
         xyz = valid = counts = None
         if cloud:
             _, T12 = ops.compose_poses(rel, None, want_T12=True)
+            # ONE pass over the depth map: back-projection + SE(3) + validity + the metric partial sums
             if fused is not None:
                 # the kernel's stores ARE the all-gather (no collective in the step; CloudGather.complete() orders a reader
                 # of the whole gathered cloud after all writers)
-                xa, va, ca = fused.backproject(depth, k4, T12[1:])
+                xa, va, ca, part = fused.backproject(depth, k4, T12[1:], gt=gt, min_depth=1e-6, max_depth=20.0)
                 xyz, valid, counts = xa[rank * B:(rank + 1) * B], va[rank * B:(rank + 1) * B], ca[rank * B:(rank + 1) * B]
             else:
-                xyz, valid, counts = ops.backproject(depth, k4, T12[1:], out_xyz=xyz_buf[i % 2])
+                xyz, valid, counts, part = ops.backproject_metrics(depth, gt, k4, T12[1:], 1e-6, 20.0, out_xyz=xyz_buf[i % 2])
                 if cloud_all is not None:
                     dist.all_gather_into_tensor(cloud_all.view(-1), xyz.view(-1))
                     dist.all_gather_into_tensor(mask_all.view(-1), valid.view(-1))
-            part = evaluation.metric_partials(depth[:, None], gt, 1e-6, 20.0)
         else:
             part = evaluation.metric_partials(depth[:, None], gt, 1e-6, 20.0)           # compute_errors / test_step
             ops.depth_metric_partials(depth[:, None].contiguous(), gt, 0.0, 0.0, 1, True)  # calculate_metrics per frame
@@ -576,6 +576,7 @@ def main():
     }
     if gather_verified is not None:
         out["gather_verified"] = gather_verified
+    # (config 3 / 5: the metric sums ride in the back-projection pass -- its 21 B/px are in "backproject")
     for key, name in (("backproject", "roofline_backproject"), ("depth_metrics", "roofline_depth_metrics")):
         bp = prof.get(key)
         if bp and bp["ms"] > 0:

@@ -45,6 +45,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_backproject_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
                                         C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_i64, c_void_p]),
+    "dav2_backproject_metrics": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
+                                         C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_i64,
+                                         c_float, c_float, c_int, c_void_p, c_void_p]),
     "dav2_peer_alloc": (c_int, [C.POINTER(c_void_p), c_i64]),
     "dav2_peer_free": (c_int, [c_void_p]),
     "dav2_peer_export": (c_int, [c_void_p, c_void_p]),

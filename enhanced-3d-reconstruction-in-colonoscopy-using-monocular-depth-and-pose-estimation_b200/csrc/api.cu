@@ -107,26 +107,46 @@ int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const 
   return launch_backproject(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, xyz, valid, counts, S(stream));
 }
 
-int dav2_backproject_gather(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
-                            const double* T12, float depth_scale, float depth_trunc, float* const* xyz_dst,
-                            uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset,
-                            void* stream) {
-  if (int rc = require_sm100()) return rc;
+static int backproject_dsts(const char* who, int32_t H, int32_t W, float* const* xyz_dst, uint8_t* const* valid_dst,
+                            int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset, float** x, uint8_t** v, int** c) {
   if (!xyz_dst || n_dst < 1 || n_dst > 8 || frame_offset < 0 || H <= 0 || W <= 0) {
-    dav2::set_last_error("backproject_gather: bad destination list");
+    dav2::set_last_error("%s: bad destination list", who);
     return -2;
   }
   const long long HW = (long long)H * W;
-  float* x[8];
-  uint8_t* v[8];
-  int* c[8];
   for (int p = 0; p < n_dst; ++p) {
     x[p] = xyz_dst[p] ? xyz_dst[p] + frame_offset * HW * 3 : nullptr;
     v[p] = (valid_dst && valid_dst[p]) ? valid_dst[p] + frame_offset * HW : nullptr;
     c[p] = (counts_dst && counts_dst[p]) ? counts_dst[p] + frame_offset : nullptr;
   }
+  return 0;
+}
+
+int dav2_backproject_gather(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,
+                            const double* T12, float depth_scale, float depth_trunc, float* const* xyz_dst,
+                            uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset,
+                            void* stream) {
+  if (int rc = require_sm100()) return rc;
+  float* x[8];
+  uint8_t* v[8];
+  int* c[8];
+  if (int rc = backproject_dsts("backproject_gather", H, W, xyz_dst, valid_dst, counts_dst, n_dst, frame_offset, x, v, c)) return rc;
   return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, x, valid_dst ? v : nullptr,
                                   counts_dst ? c : nullptr, n_dst, S(stream));
+}
+
+int dav2_backproject_metrics(const float* depth, const float* gt, int32_t B, int32_t H, int32_t W, const double* K4,
+                             int32_t k_per_frame, const double* T12, float depth_scale, float depth_trunc,
+                             float* const* xyz_dst, uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst,
+                             int64_t frame_offset, float lo, float hi, int32_t per_frame, double* partials, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  DAV2_CHECK(gt && partials, "backproject_metrics: null gt / partials");
+  float* x[8];
+  uint8_t* v[8];
+  int* c[8];
+  if (int rc = backproject_dsts("backproject_metrics", H, W, xyz_dst, valid_dst, counts_dst, n_dst, frame_offset, x, v, c)) return rc;
+  return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, x, valid_dst ? v : nullptr,
+                                  counts_dst ? c : nullptr, n_dst, S(stream), gt, lo, hi, per_frame, partials);
 }
 
 // ---- peer-mapped buffers (CUDA IPC) for the fused gather ----

@@ -26,7 +26,8 @@ int launch_attention(const h16* qkv, h16* out, int B, int N, int D, int fmt, cud
 // geometry.cu
 int launch_backproject_multi(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
                              float depth_scale, float depth_trunc, float* const* xyz, uint8_t* const* valid,
-                             int* const* counts, int n_dst, cudaStream_t stream);
+                             int* const* counts, int n_dst, cudaStream_t stream, const float* gt = nullptr, float lo = 0.f,
+                             float hi = 0.f, int per_frame = 0, double* partials = nullptr);
 int launch_backproject(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
                        float depth_scale, float depth_trunc, float* xyz, uint8_t* valid, int* counts,
                        cudaStream_t stream);

@@ -36,25 +36,65 @@ struct BpDst {
 // 20+ fp64 operations of the literal formula (the first versions were fp64-issue bound: 90 instructions / pixel,
 // 55 % issue at 33 % occupancy, 3.0 TB/s).  Differences to the oracle's operation order are ~1e-16 relative, far below
 // the single rounding to fp32 at the end.  Without a pose R = I, t = 0.
+// Validity (z = d / depth_scale in fp64; 0 < z < depth_trunc; finite) is decided on the fp32 depth itself: z is monotone
+// in d, so one lane finds the smallest float d_thr whose z reaches depth_trunc and every pixel tests 0 < d < d_thr
+// (d_thr = +inf without truncation, which still rejects inf / NaN) -- two FSETP instead of an F2F, two DSETP and a class
+// test per pixel.
 struct BpFrame {
   double dx[3], dy[3], r0[3], wrap[3], t[3];  // wrap = dy - W*dx: step from (u, v) to (u - W, v + 1)
-  double inv_scale, trunc;
+  double inv_scale;
+  float d_thr;
 };
 
+__device__ __forceinline__ void bp_frame_setup(BpFrame& fs, int c, const double* K, const double* T12, int b, int W,
+                                               double inv_scale, double trunc) {
+  // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then multiplies differs by <= 1 ulp(fp64)
+  const double fx_inv = 1.0 / K[0], fy_inv = 1.0 / K[1], cx = K[2], cy = K[3];
+  const bool hasT = T12 != nullptr;
+  const double r0c = hasT ? T12[12 * b + 4 * c] : (c == 0 ? 1.0 : 0.0), r1c = hasT ? T12[12 * b + 4 * c + 1] : (c == 1 ? 1.0 : 0.0),
+               r2c = hasT ? T12[12 * b + 4 * c + 2] : (c == 2 ? 1.0 : 0.0);
+  fs.dx[c] = r0c * fx_inv;
+  fs.dy[c] = r1c * fy_inv;
+  fs.r0[c] = r2c - cx * (r0c * fx_inv) - cy * (r1c * fy_inv);
+  fs.wrap[c] = r1c * fy_inv - (double)W * (r0c * fx_inv);
+  fs.t[c] = hasT ? T12[12 * b + 4 * c + 3] : 0.0;
+  if (c == 0) {
+    fs.inv_scale = inv_scale;
+    float thr = INFINITY;
+    if (trunc < (double)INFINITY) {  // smallest float whose z = (double)d * inv_scale is >= trunc
+      thr = (float)(trunc / inv_scale);
+      for (int i = 0; i < 4 && (double)thr * inv_scale < trunc; ++i) thr = nextafterf(thr, INFINITY);
+      for (int i = 0; i < 4 && (double)nextafterf(thr, -INFINITY) * inv_scale >= trunc; ++i) thr = nextafterf(thr, -INFINITY);
+    }
+    fs.d_thr = thr;
+  }
+}
+
+// select without a branch: the compiler otherwise sinks the three DFMA + F2F of a pixel under `if (ok)` and pays
+// BSSY / BRA / BSYNC + zero-initialisation per pixel although nearly every pixel is valid
+__device__ __forceinline__ float sel_or_zero(float v, bool ok) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tselp.f32 %0, %1, 0f00000000, p;\n\t}" : "=f"(r) : "f"(v), "r"((unsigned)ok));
+  return r;
+}
+
 __device__ __forceinline__ bool backproject_one(float d, const double (&ray)[3], const BpFrame& f, float& X, float& Y, float& Z) {
+  const bool ok = (d > 0.f) && (d < f.d_thr);  // NaN fails both; +-inf fails one of them
   const double z = (double)d * f.inv_scale;
-  const bool ok = (z > 0.0) && (z < f.trunc) && isfinite(d);  // NaN fails z > 0
-  X = ok ? (float)fma(z, ray[0], f.t[0]) : 0.f;
-  Y = ok ? (float)fma(z, ray[1], f.t[1]) : 0.f;
-  Z = ok ? (float)fma(z, ray[2], f.t[2]) : 0.f;
+  X = sel_or_zero((float)fma(z, ray[0], f.t[0]), ok);
+  Y = sel_or_zero((float)fma(z, ray[1], f.t[1]), ok);
+  Z = sel_or_zero((float)fma(z, ray[2], f.t[2]), ok);
   return ok;
 }
 
-// 4 consecutive pixels starting at linear index p0 (row-major); returns the number of valid ones
+// 4 consecutive pixels starting at linear index p0 (row-major); returns the number of valid ones.
+// CROSS = false: the caller knows that no quad of the warp straddles two image rows (7 of 8 warps at W = 518).
+template <bool CROSS>
 __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, int W, unsigned wmagic, const BpFrame& f,
                                                 float (&o)[12], uchar4& m) {
-  // v = p0 / W: multiply-high by ceil(2^32 / W) is exact while p0 * W < 2^32 (checked by the launcher)
-  const unsigned v = wmagic ? __umulhi(p0, wmagic) : p0 / (unsigned)W;
+  // v = p0 / W: multiply-high by ceil(2^32 / W) is exact while p0 * W < 2^32 (the launcher sends larger frames to the
+  // scalar kernel)
+  const unsigned v = __umulhi(p0, wmagic);
   const int u = (int)(p0 - v * (unsigned)W);
   const int nrow = W - u;  // pixels k >= nrow of the quad are on row v + 1 (at most one row change: W >= 4)
   const double ud = (double)u, vd = (double)(int)v;
@@ -62,191 +102,24 @@ __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, in
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     ra[c] = fma(ud, f.dx[c], fma(vd, f.dy[c], f.r0[c]));
-    rb[c] = ra[c] + f.wrap[c];
+    if (CROSS) rb[c] = ra[c] + f.wrap[c];
   }
   const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
   uint8_t* mm = &m.x;
   int nvalid = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const bool same = k < nrow;
     double ray[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) ray[c] = fma((double)k, f.dx[c], same ? ra[c] : rb[c]);
+    for (int c = 0; c < 3; ++c) {
+      const double base = (!CROSS || k < nrow) ? ra[c] : rb[c];
+      ray[c] = k == 0 ? base : fma((double)k, f.dx[c], base);  // (fma(0, dx, base) is not folded: dx could be inf / NaN)
+    }
     const bool ok = backproject_one(dd[k], ray, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
     mm[k] = ok ? 1 : 0;
     nvalid += ok ? 1 : 0;
   }
   return nvalid;
-}
-
-// MULTI = false: one destination (dst.*[0]); the destination loop over a runtime count made the compiler keep eight sets
-// of predicated 64-bit address arithmetic alive in the single-destination kernel as well.
-template <bool VEC4, bool MULTI>
-__global__ void __launch_bounds__(256, 3) backproject_kernel(const float* __restrict__ depth, int H, int W, unsigned wmagic,
-                                                             const double* __restrict__ K4, int k_per_frame,
-                                                             const double* __restrict__ T12, double inv_scale,
-                                                             double trunc, const BpDst dst) {
-  const int b = blockIdx.y;
-  const long long HW = (long long)H * W;
-  const double* K = K4 + (k_per_frame ? 4 * b : 0);
-  // the frame constants (two fp64 divisions, ~150 instructions) are computed by three lanes and broadcast through
-  // shared memory; per thread that prologue cost a third of the 8-pixel body
-  __shared__ BpFrame fs;
-  if (threadIdx.x < 3) {
-    // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then multiplies differs by <= 1 ulp(fp64)
-    const int c = threadIdx.x;
-    const double fx_inv = 1.0 / K[0], fy_inv = 1.0 / K[1], cx = K[2], cy = K[3];
-    const bool hasT = T12 != nullptr;
-    const double r0c = hasT ? T12[12 * b + 4 * c] : (c == 0 ? 1.0 : 0.0), r1c = hasT ? T12[12 * b + 4 * c + 1] : (c == 1 ? 1.0 : 0.0),
-                 r2c = hasT ? T12[12 * b + 4 * c + 2] : (c == 2 ? 1.0 : 0.0);
-    fs.dx[c] = r0c * fx_inv;
-    fs.dy[c] = r1c * fy_inv;
-    fs.r0[c] = r2c - cx * (r0c * fx_inv) - cy * (r1c * fy_inv);
-    fs.wrap[c] = r1c * fy_inv - (double)W * (r0c * fx_inv);
-    fs.t[c] = hasT ? T12[12 * b + 4 * c + 3] : 0.0;
-    if (c == 0) {
-      fs.inv_scale = inv_scale;
-      fs.trunc = trunc;
-    }
-  }
-  const float* dfrm = depth + b * HW;
-  const long long ooff = b * HW * 3, voff = b * HW;
-  const bool has_valid = dst.valid[0] != nullptr;
-  const int ndst = MULTI ? dst.n : 1;
-  int nvalid = 0;
-  bool have_f = false;
-  BpFrame f;
-  if (VEC4) {
-    const unsigned nvec = (unsigned)(HW >> 2);
-    // Each thread's 4 points are 48 contiguous bytes; storing them directly makes every warp-wide store touch 12 lines
-    // with 16 of every 48 bytes (ncu: 1.94x the ideal number of L2 store sectors).  Stage the warp's 1536 bytes in
-    // shared memory (48-byte thread stride = conflict-free for 128-bit accesses) and write three fully coalesced
-    // 512-byte rows instead.
-    __shared__ float4 stage[8][96];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // a block owns 512 consecutive float4s per trip; thread t takes t and t + 256 (both loads in flight before any math)
-    for (unsigned base = blockIdx.x * 512u; base < nvec; base += gridDim.x * 512u) {
-      const unsigned i0 = base + threadIdx.x, i1 = i0 + 256u;
-      const bool h0 = i0 < nvec, h1 = i1 < nvec;
-      float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
-      if (h0) d0 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i0);
-      if (h1) d1 = __ldcs(reinterpret_cast<const float4*>(dfrm) + i1);
-      if (!have_f) {  // block-uniform; the depth loads above are already in flight
-        __syncthreads();
-        f = fs;
-        have_f = true;
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const unsigned iv = half ? i1 : i0;
-        const unsigned wbase = iv - lane;  // first float4 index of this warp's 32
-        if (wbase >= nvec) continue;       // warp-uniform
-        float o[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uchar4 m = make_uchar4(0, 0, 0, 0);
-        if (iv < nvec) nvalid += backproject_quad(half ? d1 : d0, iv * 4u, W, wmagic, f, o, m);
-        stage[warp][3 * lane] = make_float4(o[0], o[1], o[2], o[3]);
-        stage[warp][3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
-        stage[warp][3 * lane + 2] = make_float4(o[8], o[9], o[10], o[11]);
-        __syncwarp();
-        const float4 r0 = stage[warp][lane], r1 = stage[warp][lane + 32], r2 = stage[warp][lane + 64];
-        __syncwarp();
-        const unsigned nout = 3u * min(32u, nvec - wbase);  // float4s of this warp inside the frame
-        for (int p = 0; p < ndst; ++p) {
-          float4* op = reinterpret_cast<float4*>(dst.xyz[p] + ooff) + 3ll * wbase;
-          if ((unsigned)lane < nout) __stcs(op + lane, r0);
-          if ((unsigned)lane + 32u < nout) __stcs(op + lane + 32, r1);
-          if ((unsigned)lane + 64u < nout) __stcs(op + lane + 64, r2);
-          if (has_valid && iv < nvec) __stcs(reinterpret_cast<uchar4*>(dst.valid[p] + voff) + iv, m);
-        }
-      }
-    }
-  } else {
-    __syncthreads();
-    f = fs;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-      const int v = (int)(i / W), u = (int)(i - (long long)v * W);
-      float X, Y, Z;
-      double ray[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) ray[c] = fma((double)u, f.dx[c], fma((double)v, f.dy[c], f.r0[c]));
-      const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z);
-      for (int p = 0; p < ndst; ++p) {
-        float* ofrm = dst.xyz[p] + ooff;
-        ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
-        if (has_valid) dst.valid[p][voff + i] = ok ? 1 : 0;
-      }
-      nvalid += ok ? 1 : 0;
-    }
-  }
-  if (dst.counts[0]) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-    __shared__ int wsum[8];
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = nvalid;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int s = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
-      if (s)
-        for (int p = 0; p < ndst; ++p) atomicAdd(dst.counts[p] + b, s);  // peer destinations: NVLink atomics
-    }
-  }
-}
-
-// xyz / valid / counts: n_dst destination pointers each (valid, counts: all NULL or all set), already offset to the
-// first frame this launch writes.
-int launch_backproject_multi(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
-                             float depth_scale, float depth_trunc, float* const* xyz, uint8_t* const* valid,
-                             int* const* counts, int n_dst, cudaStream_t stream) {
-  DAV2_CHECK(depth && xyz && K4 && B > 0 && H > 0 && W > 0, "backproject: null pointer or empty shape");
-  DAV2_CHECK(n_dst >= 1 && n_dst <= BP_MAX_DST, "backproject: 1..%d destinations", BP_MAX_DST);
-  DAV2_CHECK(depth_scale > 0.f, "backproject: depth_scale must be > 0");
-  const long long HW = (long long)H * W;
-  DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
-  BpDst dst;
-  // the 4-pixel path assumes at most ONE row change inside a quad (backproject_quad): frames narrower than 4 pixels take
-  // the scalar path
-  bool vec = (HW % 4 == 0) && (W >= 4) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
-  for (int p = 0; p < BP_MAX_DST; ++p) {
-    const bool on = p < n_dst;
-    dst.xyz[p] = on ? xyz[p] : nullptr;
-    dst.valid[p] = (on && valid) ? valid[p] : nullptr;
-    dst.counts[p] = (on && counts) ? counts[p] : nullptr;
-    if (on) {
-      DAV2_CHECK(dst.xyz[p] && (!valid || dst.valid[p]) && (!counts || dst.counts[p]), "backproject: null destination %d", p);
-      vec = vec && ((reinterpret_cast<uintptr_t>(dst.xyz[p]) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst.valid[p]) & 3) == 0);
-      // zero this launch's slice of every destination's count vector (peer pointers are mapped: stream-ordered memset)
-      if (dst.counts[p]) DAV2_CUDA_OK(cudaMemsetAsync(dst.counts[p], 0, sizeof(int) * B, stream));
-    }
-  }
-  dst.n = n_dst;
-  const double inv_scale = 1.0 / (double)depth_scale;
-  const double trunc = (double)depth_trunc;  // +inf disables truncation
-  // multiply-high division by W is exact for p < 2^32 / W  (p < HW); otherwise the kernel divides
-  const unsigned wmagic = (W > 1 && HW * (long long)W < (1ll << 32)) ? (unsigned)((1ull << 32) / (unsigned)W + 1ull) : 0u;
-  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
-  // one trip per block wherever the grid allows it: a block-stride loop with a fractional number of passes leaves
-  // most SMs idle during the last one (the first version: 3.5 passes)
-  if (bx > 1048576) bx = 1048576;
-  if (bx < 1) bx = 1;
-  ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * (4.0 + n_dst * (valid ? 13.0 : 12.0)), stream);
-  dim3 grid((unsigned)bx, (unsigned)B);
-  if (vec && n_dst == 1)
-    backproject_kernel<true, false><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
-  else if (vec)
-    backproject_kernel<true, true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
-  else
-    backproject_kernel<false, true><<<grid, 256, 0, stream>>>(depth, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst);
-  DAV2_LAUNCH_OK();
-  return 0;
-}
-
-int launch_backproject(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
-                       float depth_scale, float depth_trunc, float* xyz, uint8_t* valid, int* counts,
-                       cudaStream_t stream) {
-  return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, &xyz, valid ? &valid : nullptr,
-                                  counts ? &counts : nullptr, 1, stream);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -348,6 +221,270 @@ __device__ __forceinline__ void metric_fold(MetricAcc& a, const MetricAccF& c) {
   a.n += c.n; a.na += c.na; a.nb += c.nb; a.nc += c.nc;
 }
 
+int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW, float lo, float hi, int variant,
+                         int per_frame, double* partials, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// back-projection kernels
+// ----------------------------------------------------------------------------------------------
+// block-wide sum of per-thread metric accumulators -> 8 fp64 atomics.
+// fp64 inputs (the stand-alone metric kernel: a thread has already folded several trips): butterfly in fp64.
+__device__ __forceinline__ void metric_block_reduce(const MetricAcc& a, double* __restrict__ dst) {
+  // warp reduce: one REDUX per integer count, butterfly shuffles for the four fp64 sums
+  double v[8] = {(double)__reduce_add_sync(0xffffffffu, a.n), a.s_abs, a.s_rel, a.s_sq, a.s_gt,
+                 (double)__reduce_add_sync(0xffffffffu, a.na), (double)__reduce_add_sync(0xffffffffu, a.nb),
+                 (double)__reduce_add_sync(0xffffffffu, a.nc)};
+#pragma unroll
+  for (int k = 1; k < 5; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __shared__ double sm[8][8];
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 8; ++k) sm[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w][threadIdx.x];
+    atomicAdd(dst + threadIdx.x, s);
+  }
+}
+// fp32 inputs (the fused kernel: 8 pixels per thread): the warp's 256 pixels are summed with fp32 shuffles (20 SHFL +
+// 20 FADD per thread instead of 40 + 20 DADD -- the fp64 butterfly was a fifth of the fused kernel's instructions), the
+// eight warp sums and everything after them stay fp64.  256 terms in fp32: <= 2e-6 relative on a warp sum, random in sign.
+__device__ __forceinline__ void metric_block_reduce(const MetricAccF& a, double* __restrict__ dst) {
+  float v[4] = {a.s_abs, a.s_rel, a.s_sq, a.s_gt};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  const unsigned n = __reduce_add_sync(0xffffffffu, a.n), na = __reduce_add_sync(0xffffffffu, a.na),
+                 nb = __reduce_add_sync(0xffffffffu, a.nb), nc = __reduce_add_sync(0xffffffffu, a.nc);
+  __shared__ double sm[8][8];
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sm[warp][0] = (double)n; sm[warp][1] = (double)v[0]; sm[warp][2] = (double)v[1]; sm[warp][3] = (double)v[2];
+    sm[warp][4] = (double)v[3]; sm[warp][5] = (double)na; sm[warp][6] = (double)nb; sm[warp][7] = (double)nc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w][threadIdx.x];
+    atomicAdd(dst + threadIdx.x, s);
+  }
+}
+
+// Vector path: a block owns 512 consecutive float4s (2048 pixels) of ONE frame; thread t takes quads t and t + 256, all
+// loads (depth, and gt when the metric sums ride along) in flight before any math.  Each thread's 4 points are 48
+// contiguous bytes; storing them directly makes every warp-wide store touch 12 lines with 16 of every 48 bytes (ncu:
+// 1.94x the ideal number of L2 store sectors), so the warp stages its 1536 bytes in shared memory (48-byte thread stride =
+// conflict-free for 128-bit accesses) and writes three fully coalesced 512-byte rows.
+// MULTI = false: one destination (dst.*[0]); a destination loop over a runtime count kept eight sets of predicated 64-bit
+// address arithmetic alive in the single-destination kernel as well.
+// METRICS = true (round 2): the test_step metric partial sums (variant 0: lo <= gt <= hi, eval/evaluation.py:16-60) are
+// accumulated from the SAME depth registers -- the separate metric kernel re-read the 68.7 MB depth map the head conv had
+// just written (8 B/px of its own traffic); fused, one pass moves 21 B/px instead of 17 + 8.
+template <bool MULTI, bool METRICS>
+__global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __restrict__ depth, const float* __restrict__ gt,
+                                                                 int H, int W, unsigned wmagic, const double* __restrict__ K4,
+                                                                 int k_per_frame, const double* __restrict__ T12,
+                                                                 double inv_scale, double trunc, const BpDst dst, float lo,
+                                                                 float hi, int per_frame, double* __restrict__ partials) {
+  const int b = blockIdx.y;
+  const long long HW = (long long)H * W;
+  // the frame constants (two fp64 divisions, ~150 instructions) are computed by three lanes and broadcast through
+  // shared memory; per thread that prologue cost a third of the 8-pixel body
+  __shared__ BpFrame fs;
+  __shared__ float4 stage[8][96];
+  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, trunc);
+  const float4* dfrm = reinterpret_cast<const float4*>(depth + b * HW);
+  const float4* gfrm = METRICS ? reinterpret_cast<const float4*>(gt + b * HW) : nullptr;
+  const long long ooff = b * HW * 3, voff = b * HW;
+  const bool has_valid = dst.valid[0] != nullptr;
+  const int ndst = MULTI ? dst.n : 1;
+  const unsigned nvec = (unsigned)(HW >> 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned i0 = blockIdx.x * 512u + threadIdx.x, i1 = i0 + 256u;
+  const bool h0 = i0 < nvec, h1 = i1 < nvec;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 d0 = zero, d1 = zero, g0 = zero, g1 = zero;
+  if (h0) d0 = __ldcs(dfrm + i0);
+  if (h1) d1 = __ldcs(dfrm + i1);
+  if (METRICS) {
+    if (h0) g0 = __ldcs(gfrm + i0);
+    if (h1) g1 = __ldcs(gfrm + i1);
+  }
+  __syncthreads();  // frame constants; the loads above are already in flight
+  int nvalid = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const unsigned iv = half ? i1 : i0;
+    const unsigned wbase = iv - lane;  // first float4 index of this warp's 32
+    if (wbase >= nvec) continue;       // warp-uniform
+    float o[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uchar4 m = make_uchar4(0, 0, 0, 0);
+    if (iv < nvec) {
+      // does any quad of this warp straddle two rows?  first pixel of the warp's span: wbase*4, 128 pixels long
+      const unsigned pw = wbase * 4u;
+      const unsigned vw = __umulhi(pw, wmagic);
+      const bool cross = (pw - vw * (unsigned)W) + 128u > (unsigned)W;  // warp-uniform
+      if (cross) nvalid += backproject_quad<true>(half ? d1 : d0, iv * 4u, W, wmagic, fs, o, m);
+      else nvalid += backproject_quad<false>(half ? d1 : d0, iv * 4u, W, wmagic, fs, o, m);
+    }
+    stage[warp][3 * lane] = make_float4(o[0], o[1], o[2], o[3]);
+    stage[warp][3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    stage[warp][3 * lane + 2] = make_float4(o[8], o[9], o[10], o[11]);
+    __syncwarp();
+    const float4 r0 = stage[warp][lane], r1 = stage[warp][lane + 32], r2 = stage[warp][lane + 64];
+    __syncwarp();
+    const unsigned nout = 3u * min(32u, nvec - wbase);  // float4s of this warp inside the frame
+    for (int p = 0; p < ndst; ++p) {
+      float4* op = reinterpret_cast<float4*>(dst.xyz[p] + ooff) + 3ll * wbase;
+      if ((unsigned)lane < nout) __stcs(op + lane, r0);
+      if ((unsigned)lane + 32u < nout) __stcs(op + lane + 32, r1);
+      if ((unsigned)lane + 64u < nout) __stcs(op + lane + 64, r2);
+      if (has_valid && iv < nvec) __stcs(reinterpret_cast<uchar4*>(dst.valid[p] + voff) + iv, m);
+    }
+  }
+  if (dst.counts[0]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    __shared__ int wsum[8];
+    if (lane == 0) wsum[warp] = nvalid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int w = 0; w < 8; ++w) s += wsum[w];
+      if (s)
+        for (int p = 0; p < ndst; ++p) atomicAdd(dst.counts[p] + b, s);  // peer destinations: NVLink atomics
+    }
+  }
+  if (METRICS) {
+    MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
+    // zero-filled (absent) quads are invalid under the variant-0 mask as long as lo > 0; h0 / h1 guard the general case
+    const bool exact = max(h0 ? metric_exact_key<0>(d0, g0, lo, hi) : 0u, h1 ? metric_exact_key<0>(d1, g1, lo, hi) : 0u) >= 0x7f7fffffu;
+    if (!exact) {
+      if (h0) metric_quad<0, false>(c, d0, g0, lo, hi);
+      if (h1) metric_quad<0, false>(c, d1, g1, lo, hi);
+    } else {
+      if (h0) metric_quad<0, true>(c, d0, g0, lo, hi);
+      if (h1) metric_quad<0, true>(c, d1, g1, lo, hi);
+    }
+    metric_block_reduce(c, partials + (per_frame ? 8 * b : 0));
+  }
+}
+
+// Scalar path (frames whose pixel count is not a multiple of 4, narrower than 4 pixels, or unaligned buffers)
+__global__ void __launch_bounds__(256) backproject_scalar_kernel(const float* __restrict__ depth, int H, int W,
+                                                                 const double* __restrict__ K4, int k_per_frame,
+                                                                 const double* __restrict__ T12, double inv_scale, double trunc,
+                                                                 const BpDst dst) {
+  const int b = blockIdx.y;
+  const long long HW = (long long)H * W;
+  __shared__ BpFrame fs;
+  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, trunc);
+  __syncthreads();
+  const BpFrame f = fs;
+  const float* dfrm = depth + b * HW;
+  const long long ooff = b * HW * 3, voff = b * HW;
+  const bool has_valid = dst.valid[0] != nullptr;
+  int nvalid = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i / W), u = (int)(i - (long long)v * W);
+    float X, Y, Z;
+    double ray[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ray[c] = fma((double)u, f.dx[c], fma((double)v, f.dy[c], f.r0[c]));
+    const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z);
+    for (int p = 0; p < dst.n; ++p) {
+      float* ofrm = dst.xyz[p] + ooff;
+      ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
+      if (has_valid) dst.valid[p][voff + i] = ok ? 1 : 0;
+    }
+    nvalid += ok ? 1 : 0;
+  }
+  if (dst.counts[0]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    __shared__ int wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = nvalid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+      if (s)
+        for (int p = 0; p < dst.n; ++p) atomicAdd(dst.counts[p] + b, s);
+    }
+  }
+}
+
+// xyz / valid / counts: n_dst destination pointers each (valid, counts: all NULL or all set), already offset to the
+// first frame this launch writes.  gt / partials non-NULL: the variant-0 metric partial sums of (depth, gt) are produced
+// by the same pass (partials is zeroed here; fp64 [B,8] if per_frame else [8]).
+int launch_backproject_multi(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
+                             float depth_scale, float depth_trunc, float* const* xyz, uint8_t* const* valid,
+                             int* const* counts, int n_dst, cudaStream_t stream, const float* gt, float lo, float hi,
+                             int per_frame, double* partials) {
+  DAV2_CHECK(depth && xyz && K4 && B > 0 && H > 0 && W > 0, "backproject: null pointer or empty shape");
+  DAV2_CHECK(n_dst >= 1 && n_dst <= BP_MAX_DST, "backproject: 1..%d destinations", BP_MAX_DST);
+  DAV2_CHECK(depth_scale > 0.f, "backproject: depth_scale must be > 0");
+  DAV2_CHECK((gt == nullptr) == (partials == nullptr), "backproject: gt and partials go together");
+  const long long HW = (long long)H * W;
+  DAV2_CHECK(HW < (1ll << 31), "backproject: frame larger than 2^31 pixels");
+  BpDst dst;
+  // the 4-pixel path assumes at most ONE row change inside a quad (backproject_quad): frames narrower than 4 pixels take
+  // the scalar path
+  // multiply-high division by W (vector path) is exact for p < 2^32 / W, p < HW
+  const unsigned wmagic = (W > 1 && HW * (long long)W < (1ll << 32)) ? (unsigned)((1ull << 32) / (unsigned)W + 1ull) : 0u;
+  bool vec = (HW % 4 == 0) && (W >= 4) && wmagic != 0u && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(gt) & 15) == 0);
+  for (int p = 0; p < BP_MAX_DST; ++p) {
+    const bool on = p < n_dst;
+    dst.xyz[p] = on ? xyz[p] : nullptr;
+    dst.valid[p] = (on && valid) ? valid[p] : nullptr;
+    dst.counts[p] = (on && counts) ? counts[p] : nullptr;
+    if (on) {
+      DAV2_CHECK(dst.xyz[p] && (!valid || dst.valid[p]) && (!counts || dst.counts[p]), "backproject: null destination %d", p);
+      vec = vec && ((reinterpret_cast<uintptr_t>(dst.xyz[p]) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst.valid[p]) & 3) == 0);
+      // zero this launch's slice of every destination's count vector (peer pointers are mapped: stream-ordered memset)
+      if (dst.counts[p]) DAV2_CUDA_OK(cudaMemsetAsync(dst.counts[p], 0, sizeof(int) * B, stream));
+    }
+  }
+  dst.n = n_dst;
+  const double inv_scale = 1.0 / (double)depth_scale;
+  const double trunc = (double)depth_trunc;  // +inf disables truncation
+  if (gt && !vec) {
+    // unaligned / odd-sized frames: the two passes run separately (same results)
+    if (int rc = launch_depth_metrics(depth, gt, B, HW, lo, hi, 0, per_frame, partials, stream)) return rc;
+    gt = nullptr;
+    partials = nullptr;
+  }
+  if (gt) DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
+  // one trip per block: a block-stride loop with a fractional number of passes leaves most SMs idle during the last one
+  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
+  if (bx > 1048576) bx = 1048576;
+  if (bx < 1) bx = 1;
+  ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * ((gt ? 8.0 : 4.0) + n_dst * (valid ? 13.0 : 12.0)), stream);
+  dim3 grid((unsigned)bx, (unsigned)B);
+#define DAV2_BP_GO(MULTI, MET) \
+  backproject_vec_kernel<MULTI, MET><<<grid, 256, 0, stream>>>(depth, gt, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst, lo, hi, per_frame, partials)
+  if (vec && n_dst == 1 && gt) DAV2_BP_GO(false, true);
+  else if (vec && n_dst == 1) DAV2_BP_GO(false, false);
+  else if (vec && gt) DAV2_BP_GO(true, true);
+  else if (vec) DAV2_BP_GO(true, false);
+  else backproject_scalar_kernel<<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, trunc, dst);
+#undef DAV2_BP_GO
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+int launch_backproject(const float* depth, int B, int H, int W, const double* K4, int k_per_frame, const double* T12,
+                       float depth_scale, float depth_trunc, float* xyz, uint8_t* valid, int* counts,
+                       cudaStream_t stream) {
+  return launch_backproject_multi(depth, B, H, W, K4, k_per_frame, T12, depth_scale, depth_trunc, &xyz, valid ? &valid : nullptr,
+                                  counts ? &counts : nullptr, 1, stream, nullptr, 0.f, 0.f, 0, nullptr);
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(256, 4) depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                                long long HW, float lo, float hi, int per_frame,
@@ -387,24 +524,7 @@ __global__ void __launch_bounds__(256, 4) depth_metrics_kernel(const float* __re
       metric_fold(a, c);
     }
   }
-  // warp reduce: one REDUX per integer count, butterfly shuffles for the four fp64 sums
-  double v[8] = {(double)__reduce_add_sync(0xffffffffu, a.n), a.s_abs, a.s_rel, a.s_sq, a.s_gt,
-                 (double)__reduce_add_sync(0xffffffffu, a.na), (double)__reduce_add_sync(0xffffffffu, a.nb),
-                 (double)__reduce_add_sync(0xffffffffu, a.nc)};
-#pragma unroll
-  for (int k = 1; k < 5; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  __shared__ double sm[8][8];
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0)
-    for (int k = 0; k < 8; ++k) sm[warp][k] = v[k];
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w][threadIdx.x];
-    atomicAdd(partials + (per_frame ? 8 * b : 0) + threadIdx.x, s);
-  }
+  metric_block_reduce(a, partials + (per_frame ? 8 * b : 0));
 }
 
 int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW, float lo, float hi, int variant,

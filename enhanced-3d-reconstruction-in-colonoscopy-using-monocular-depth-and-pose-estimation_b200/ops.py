@@ -150,10 +150,14 @@ def backproject(depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, dep
 
 
 def backproject_gather(depth: torch.Tensor, K4, T12, dst_xyz, dst_valid=None, dst_counts=None, frame_offset: int = 0,
-                       depth_scale: float = 1.0, depth_trunc: float = math.inf):
+                       depth_scale: float = 1.0, depth_trunc: float = math.inf, gt: torch.Tensor | None = None,
+                       min_depth: float = 1e-6, max_depth: float = 20.0, per_frame: bool = False):
     """Fused back-projection + all-gather store (dav2_backproject_gather): results for depth [B,H,W] are written at frame
     index ``frame_offset + b`` of EVERY destination.  dst_* are lists of device pointers (ints; peer-mapped buffers from
-    ``sharding.CloudGather``) or of tensors ([F,H*W,3] fp32 / [F,H*W] u8 / [F] i32)."""
+    ``sharding.CloudGather``) or of tensors ([F,H*W,3] fp32 / [F,H*W] u8 / [F] i32).
+
+    With ``gt`` (fp32, B*H*W elements) the SAME pass also accumulates the test_step metric partial sums of (depth, gt)
+    (dav2_backproject_metrics) and returns them (fp64 [8] or [B,8]); without, returns None."""
     require_cuda(depth, "depth")
     assert depth.dtype == torch.float32 and depth.dim() == 3
     B, H, W = depth.shape
@@ -174,10 +178,37 @@ def backproject_gather(depth: torch.Tensor, K4, T12, dst_xyz, dst_valid=None, ds
         assert len(items) == n
         return (C.c_void_p * n)(*[(t.data_ptr() if torch.is_tensor(t) else int(t)) for t in items])
 
-    check(_lib.load().dav2_backproject_gather(depth.data_ptr(), B, H, W, K4.data_ptr(), k_per_frame, _ptr(T12),
-                                              float(depth_scale), float(depth_trunc), ptr_array(dst_xyz), ptr_array(dst_valid),
-                                              ptr_array(dst_counts), n, int(frame_offset), current_stream_ptr(dev)),
-          "dav2_backproject_gather")
+    lib = _lib.load()
+    if gt is None:
+        check(lib.dav2_backproject_gather(depth.data_ptr(), B, H, W, K4.data_ptr(), k_per_frame, _ptr(T12),
+                                          float(depth_scale), float(depth_trunc), ptr_array(dst_xyz), ptr_array(dst_valid),
+                                          ptr_array(dst_counts), n, int(frame_offset), current_stream_ptr(dev)),
+              "dav2_backproject_gather")
+        return None
+    require_cuda(gt, "gt")
+    assert gt.dtype == torch.float32 and gt.numel() == depth.numel()
+    part = torch.empty((B, 8) if per_frame else (8,), dtype=torch.float64, device=dev)
+    check(lib.dav2_backproject_metrics(depth.data_ptr(), gt.data_ptr(), B, H, W, K4.data_ptr(), k_per_frame, _ptr(T12),
+                                       float(depth_scale), float(depth_trunc), ptr_array(dst_xyz), ptr_array(dst_valid),
+                                       ptr_array(dst_counts), n, int(frame_offset), float(min_depth), float(max_depth),
+                                       1 if per_frame else 0, part.data_ptr(), current_stream_ptr(dev)),
+          "dav2_backproject_metrics")
+    return part
+
+
+def backproject_metrics(depth: torch.Tensor, gt: torch.Tensor, K4, T12=None, min_depth: float = 1e-6, max_depth: float = 20.0,
+                        depth_scale: float = 1.0, depth_trunc: float = math.inf, per_frame: bool = False,
+                        out_xyz: torch.Tensor | None = None):
+    """One pass over depth [B,H,W]: (xyz [B,H*W,3], valid [B,H*W], counts [B], metric partial sums fp64 [8] | [B,8]) --
+    ``backproject`` + ``evaluation.metric_partials`` (test_step mask min_depth <= gt <= max_depth) without re-reading depth."""
+    B, H, W = depth.shape
+    dev = depth.device
+    xyz = out_xyz if out_xyz is not None else torch.empty(B, H * W, 3, dtype=torch.float32, device=dev)
+    valid = torch.empty(B, H * W, dtype=torch.uint8, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    part = backproject_gather(depth, K4, T12, [xyz], [valid], [counts], 0, depth_scale, depth_trunc, gt=gt.contiguous(),
+                              min_depth=min_depth, max_depth=max_depth, per_frame=per_frame)
+    return xyz, valid, counts, part
 
 
 def voxel_downsample(xyz: torch.Tensor, voxel_size: float, rgb: torch.Tensor | None = None,

@@ -119,19 +119,22 @@ class CloudGather:
         counts = m[self.off_counts:self.off_counts + F * 4].view(torch.int32)
         return xyz, valid, counts
 
-    def backproject(self, depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, depth_trunc: float = math.inf):
+    def backproject(self, depth: torch.Tensor, K4, T12=None, depth_scale: float = 1.0, depth_trunc: float = math.inf,
+                    gt: Optional[torch.Tensor] = None, min_depth: float = 1e-6, max_depth: float = 20.0):
         """depth [frames_per_rank,H,W] of THIS rank -> views of the gathered cloud (complete after ``complete()`` or any
-        later collective on this stream)."""
+        later collective on this stream).  With ``gt`` the same pass also produces this rank's test_step metric partial
+        sums (fp64 [8]) and the call returns (xyz, valid, counts, partials)."""
         from . import ops
         assert depth.shape[0] == self.fpr and depth.shape[1] * depth.shape[2] == self.HW
         buf = self._step % self.n_buffers
         self._step += 1
         o = buf * self.per
-        ops.backproject_gather(depth, K4, T12, [p + o for p in self.peers],
-                               [p + o + self.off_valid for p in self.peers] if self.with_valid else None,
-                               [p + o + self.off_counts for p in self.peers], frame_offset=self.rank * self.fpr,
-                               depth_scale=depth_scale, depth_trunc=depth_trunc)
-        return self.views(buf)
+        part = ops.backproject_gather(depth, K4, T12, [p + o for p in self.peers],
+                                      [p + o + self.off_valid for p in self.peers] if self.with_valid else None,
+                                      [p + o + self.off_counts for p in self.peers], frame_offset=self.rank * self.fpr,
+                                      depth_scale=depth_scale, depth_trunc=depth_trunc, gt=gt, min_depth=min_depth,
+                                      max_depth=max_depth)
+        return self.views(buf) if gt is None else self.views(buf) + (part,)
 
     def complete(self):
         """Order this stream after every rank's back-projection kernel (a 4-byte all-reduce)."""

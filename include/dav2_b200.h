@@ -114,6 +114,17 @@ int dav2_backproject_gather(const float* depth, int32_t B, int32_t H, int32_t W,
                             uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst, int64_t frame_offset,
                             void* stream);
 
+/* Back-projection AND the test_step metric partial sums in ONE pass over the depth map (round 2): the same arithmetic and
+ * destinations as dav2_backproject_gather (n_dst = 1 with one-element arrays for a purely local cloud), plus
+ * dav2_depth_metrics variant 0 (mask lo <= gt <= hi, lightning_model.py:304-313 + eval/evaluation.py:16-60) on
+ * (pred = depth, gt) -- gt device fp32 [B,H*W] -- accumulated from the registers that already hold the depth, so the
+ * 4 B/px re-read of the stand-alone metric kernel disappears (21 B/px for the fused pass instead of 17 + 8).
+ * partials device fp64 [B,8] (per_frame = 1) or [8], zeroed by the call; same slots as dav2_depth_metrics. */
+int dav2_backproject_metrics(const float* depth, const float* gt, int32_t B, int32_t H, int32_t W, const double* K4,
+                             int32_t k_per_frame, const double* T12, float depth_scale, float depth_trunc,
+                             float* const* xyz_dst, uint8_t* const* valid_dst, int32_t* const* counts_dst, int32_t n_dst,
+                             int64_t frame_offset, float lo, float hi, int32_t per_frame, double* partials, void* stream);
+
 /* Peer-mapped device buffers for dav2_backproject_gather: one process per GPU allocates its gather buffer
  * (dav2_peer_alloc: cudaMalloc, so the allocation is IPC-exportable), exports a 64-byte handle (cudaIpcGetMemHandle),
  * exchanges the handles through torch.distributed, and maps every other rank's buffer (dav2_peer_open:

@@ -81,17 +81,21 @@ if what in ("geom",):
         xyz, valid, counts = ops.backproject(depth, (170.1677, 169.8526, 194.7248, 198.2624), T12)
         ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False)
         ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 1, True)
+        ops.backproject_metrics(depth, gt, (170.1677, 169.8526, 194.7248, 198.2624), T12, 1e-6, 20.0, out_xyz=xyz)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
     k4dev = torch.tensor([170.1677, 169.8526, 194.7248, 198.2624], dtype=torch.float64, device=dev)
     T12 = T12.to(dev)
     for name, fn in (("backproject", lambda: ops.backproject(depth, k4dev, T12, out_xyz=xyz)),
-                     ("metrics0", lambda: ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False))):
+                     ("metrics0", lambda: ops.depth_metric_partials(depth, gt, 1e-6, 20.0, 0, False)),
+                     ("backproject+metrics fused (21 B/px)", lambda: ops.backproject_metrics(depth, gt, k4dev, T12, 1e-6, 20.0, out_xyz=xyz))):
         fn(); torch.cuda.synchronize()
         ev[0].record()
         for _ in range(20): fn()
         ev[1].record(); torch.cuda.synchronize()
-        print(name, "us/launch (warm, back to back)", ev[0].elapsed_time(ev[1]) / 20 * 1e3)
+        us = ev[0].elapsed_time(ev[1]) / 20 * 1e3
+        bpp = {"backproject": 17.0, "metrics0": 8.0}.get(name, 21.0)
+        print(name, "us/launch (warm, back to back) %.1f  -> %.0f GB/s algorithmic" % (us, B * H * W * bpp / us / 1e3))
     pts = xyz[:8].reshape(-1, 3)
     ev[0].record(); q, _ = ops.voxel_downsample(pts, 0.01, valid=valid[:8].reshape(-1)); ev[1].record(); torch.cuda.synchronize()
     print("voxel 8 frames", pts.shape[0], "->", q.shape[0], "ms", ev[0].elapsed_time(ev[1]))

@@ -346,3 +346,41 @@ def test_cloud_gather_two_gpus():
                         "127.0.0.1", "--master-port", "29631", os.path.join(root, "tests", "mgpu_gather_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "MGPU_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,H,W,pose", [(2, 37, 52, True), (3, 518, 518, True), (1, 70, 98, False), (2, 7, 5, True)])
+def test_backproject_metrics_fused_equals_separate(B, H, W, pose):
+    """dav2_backproject_metrics: ONE pass == dav2_backproject (bit for bit) + dav2_depth_metrics variant 0 (sums to fp32
+    accumulation order), incl. invalid / non-finite depths, the per-frame form and the odd-sized fallback (7x5)."""
+    from dav2_b200 import evaluation as ev
+    from dav2_b200 import ops
+    rng = np.random.default_rng(B * 100 + H)
+    gt = np.clip(rng.gamma(2.0, 0.15, size=(B, H, W)), 0, 1).astype(np.float32)
+    gt[rng.random((B, H, W)) < 0.02] = 0.0
+    depth = (np.where(gt > 0, gt, 0.3) * rng.normal(1.0, 0.07, size=gt.shape)).astype(np.float32)
+    depth[rng.random((B, H, W)) < 0.01] = 0.0
+    if H * W > 8:
+        depth[0].reshape(-1)[1] = np.nan
+        depth[0].reshape(-1)[2] = np.inf
+        depth[0].reshape(-1)[3] = -1.0
+    k4 = geo.scale_intrinsics(geo.SIMCOL_K_475, 475, W)
+    T12 = None
+    if pose:
+        T12 = torch.from_numpy(np.stack([geo.make_transform(rng.normal(size=3), rng.normal(size=4))[:3, :4].reshape(-1) for _ in range(B)]))
+    d, g = torch.from_numpy(depth).cuda(), torch.from_numpy(gt).cuda()
+    xyz, valid, counts = ops.backproject(d, k4, T12)
+    for per_frame in (False, True):
+        want = ops.depth_metric_partials(d, g, 1e-6, 20.0, 0, per_frame)
+        fx, fv, fc, part = ops.backproject_metrics(d, g, k4, T12, 1e-6, 20.0, per_frame=per_frame)
+        assert torch.equal(fx.view(torch.int32), xyz.view(torch.int32)) and torch.equal(fv, valid) and torch.equal(fc, counts)
+        assert part.shape == want.shape
+        w, p = want.cpu().numpy(), part.cpu().numpy()
+        assert np.array_equal(w[..., [0, 5, 6, 7]], p[..., [0, 5, 6, 7]])          # counts are exact
+        np.testing.assert_allclose(p[..., 1:5], w[..., 1:5], rtol=2e-6, atol=1e-9)  # fp32 partial sums, fp64 across warps
+    # and against the oracle, finalised (the 1e-4 metric gate)
+    _, _, _, part = ops.backproject_metrics(d, g, k4, T12, 1e-6, 20.0)
+    got = ev.finalize_compute_errors(part)
+    ref = met.test_step_metrics(depth[:, None], gt[:, None], 1e-6, 20.0)  # NaN / inf predictions poison some entries: skipped below
+    for k in CE_KEYS:
+        if np.isfinite(ref[k]):
+            assert abs(float(got[k]) - ref[k]) < METRIC_TOL * max(1.0, abs(ref[k])), (k, float(got[k]), ref[k])
