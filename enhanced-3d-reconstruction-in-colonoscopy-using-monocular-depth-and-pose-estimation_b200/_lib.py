@@ -41,6 +41,8 @@ SIGNATURES = {
     "dav2_debug_read": (c_int, [c_void_p, C.c_char_p, c_void_p, c_i64, c_void_p]),
     "dav2_resize_depth": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dav2_preprocess_bgr_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dav2_preprocess_bgr_u8_batch": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dav2_resize_aa": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
     "dav2_backproject": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_backproject_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_float,

@@ -97,7 +97,19 @@ int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float*
 
 int dav2_preprocess_bgr_u8(const uint8_t* img, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw, void* stream) {
   if (int rc = require_sm100()) return rc;
-  return launch_preprocess_bgr(img, H, W, out, nh, nw, S(stream));
+  return launch_preprocess_bgr(img, 1, H, W, out, nh, nw, S(stream));
+}
+
+int dav2_preprocess_bgr_u8_batch(const uint8_t* img, int32_t B, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw,
+                                 void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_preprocess_bgr(img, B, H, W, out, nh, nw, S(stream));
+}
+
+int dav2_resize_aa(int32_t mode, const void* in, int32_t B, int32_t H, int32_t W, float* out, int32_t Ho, int32_t Wo,
+                   float div_in, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_resample_aa(mode, in, B, H, W, out, Ho, Wo, div_in, S(stream));
 }
 
 int dav2_backproject(const float* depth, int32_t B, int32_t H, int32_t W, const double* K4, int32_t k_per_frame,

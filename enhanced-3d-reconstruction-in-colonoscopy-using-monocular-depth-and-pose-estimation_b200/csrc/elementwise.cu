@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(256) preprocess_bgr_kernel(const uint8_t* __re
                                                              int nh, int nw, double sy, double sx) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nh * nw) return;
+  img += (long long)blockIdx.y * H * W * 3;       // frame blockIdx.y of the batch
+  out += (long long)blockIdx.y * 3 * nh * nw;
   const int dy = t / nw, dx = t - dy * nw;
   float cy[4], cx[4];
   int iy[4], ix[4];
@@ -372,10 +374,106 @@ __global__ void __launch_bounds__(256) preprocess_bgr_kernel(const uint8_t* __re
   for (int c = 0; c < 3; ++c) out[c * plane + t] = (float)((acc[c] - mean[c]) / stdv[c]);
 }
 
-int launch_preprocess_bgr(const uint8_t* img, int H, int W, float* out, int nh, int nw, cudaStream_t stream) {
-  DAV2_CHECK(img && out && H > 0 && W > 0 && nh > 0 && nw > 0, "preprocess: bad arguments");
-  ProfScope ps(PC_RESAMPLE, 0.0, (double)H * W * 3.0 + (double)nh * nw * 12.0, stream);
-  preprocess_bgr_kernel<<<(nh * nw + 255) / 256, 256, 0, stream>>>(img, H, W, out, nh, nw, (double)H / nh, (double)W / nw);
+int launch_preprocess_bgr(const uint8_t* img, int B, int H, int W, float* out, int nh, int nw, cudaStream_t stream) {
+  DAV2_CHECK(img && out && B > 0 && H > 0 && W > 0 && nh > 0 && nw > 0, "preprocess: bad arguments");
+  ProfScope ps(PC_RESAMPLE, 0.0, (double)B * ((double)H * W * 3.0 + (double)nh * nw * 12.0), stream);
+  dim3 grid((unsigned)((nh * nw + 255) / 256), (unsigned)B);
+  preprocess_bgr_kernel<<<grid, 256, 0, stream>>>(img, H, W, out, nh, nw, (double)H / nh, (double)W / nw);
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Dataset pre-processing (data_processing/simcol.py:104-135,161-168): ToTensor -> Resize((S, S), BICUBIC, antialias=True)
+// [-> Normalize], i.e. torch's anti-aliased bicubic (aten _upsample_bicubic2d_aa): per output index i along an axis
+//   scale = in / out, support = 2 * max(scale, 1), center = scale * (i + 0.5),
+//   taps j in [xmin, xmin + xsize): xmin = max(int(center - support + 0.5), 0), xsize = min(int(center + support + 0.5), in) - xmin
+//   weight_j = cubic_{a = -0.5}((j - center + 0.5) / max(scale, 1)), normalised to sum 1 (borders truncate, no clamping).
+// One thread per output pixel, fp32 arithmetic like the CPU transform; the weights are recomputed in the tap loops (no
+// per-thread arrays, any scale).  Inputs are divided by div_in with an IEEE division, like `image.astype(float32) / 255.0`.
+// MODE 0: u8 [B,H,W,3] RGB / 255, ImageNet normalisation -> [B,3,Ho,Wo];
+// MODE 1: u16 [B,H,W] / 65535 -> [B,1,Ho,Wo];  MODE 2: fp32 [B,H,W] / div_in -> [B,1,Ho,Wo].
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic_aa(float x) {
+  const float a = -0.5f;
+  x = fabsf(x);
+  if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+  if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+  return 0.0f;
+}
+struct AaAxis {
+  int lo, n;
+  float center, inv, total;
+};
+__device__ __forceinline__ AaAxis aa_axis(int i, int in, float scale) {
+  AaAxis ax;
+  const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
+  ax.inv = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  ax.center = scale * ((float)i + 0.5f);
+  ax.lo = max((int)(ax.center - support + 0.5f), 0);
+  ax.n = min((int)(ax.center + support + 0.5f), in) - ax.lo;
+  float t = 0.f;
+  for (int j = 0; j < ax.n; ++j) t += cubic_aa(((float)(j + ax.lo) - ax.center + 0.5f) * ax.inv);
+  ax.total = t;
+  return ax;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) resample_aa_kernel(const void* __restrict__ in_, int H, int W, float* __restrict__ out,
+                                                          int Ho, int Wo, float sy, float sx, float div_in) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Ho * Wo) return;
+  const int oy = t / Wo, ox = t - oy * Wo;
+  const AaAxis ay = aa_axis(oy, H, sy), ax = aa_axis(ox, W, sx);
+  constexpr int C = MODE == 0 ? 3 : 1;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  const long long frame = (long long)blockIdx.y * H * W;
+  for (int r = 0; r < ay.n; ++r) {
+    const float wy = cubic_aa(((float)(r + ay.lo) - ay.center + 0.5f) * ay.inv) / ay.total;
+    float row[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) row[c] = 0.f;
+    const long long line = frame + (long long)(r + ay.lo) * W;
+    for (int k = 0; k < ax.n; ++k) {
+      const float wx = cubic_aa(((float)(k + ax.lo) - ax.center + 0.5f) * ax.inv) / ax.total;
+      const long long px = line + k + ax.lo;
+      if (MODE == 0) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(in_) + px * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) row[c] = fmaf(wx, (float)p[c] / div_in, row[c]);
+      } else if (MODE == 1) {
+        row[0] = fmaf(wx, (float)reinterpret_cast<const uint16_t*>(in_)[px] / div_in, row[0]);
+      } else {
+        row[0] = fmaf(wx, reinterpret_cast<const float*>(in_)[px] / div_in, row[0]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = fmaf(wy, row[c], acc[c]);
+  }
+  const long long plane = (long long)Ho * Wo;
+  float* o = out + (long long)blockIdx.y * C * plane + t;
+  if (MODE == 0) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * plane] = (acc[c] - mean[c]) / stdv[c];
+  } else {
+    o[0] = acc[0];
+  }
+}
+
+int launch_resample_aa(int mode, const void* in, int B, int H, int W, float* out, int Ho, int Wo, float div_in,
+                       cudaStream_t stream) {
+  DAV2_CHECK(in && out && B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && div_in != 0.f, "resample_aa: bad arguments");
+  DAV2_CHECK(mode >= 0 && mode <= 2, "resample_aa: mode must be 0 (u8 RGB image), 1 (u16 depth) or 2 (fp32 depth)");
+  const int cin = mode == 0 ? 3 : (mode == 1 ? 2 : 4), cout = mode == 0 ? 12 : 4;
+  ProfScope ps(PC_RESAMPLE, 0.0, (double)B * ((double)H * W * cin + (double)Ho * Wo * cout), stream);
+  dim3 grid((unsigned)((Ho * Wo + 255) / 256), (unsigned)B);
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  if (mode == 0) resample_aa_kernel<0><<<grid, 256, 0, stream>>>(in, H, W, out, Ho, Wo, sy, sx, div_in);
+  else if (mode == 1) resample_aa_kernel<1><<<grid, 256, 0, stream>>>(in, H, W, out, Ho, Wo, sy, sx, div_in);
+  else resample_aa_kernel<2><<<grid, 256, 0, stream>>>(in, H, W, out, Ho, Wo, sy, sx, div_in);
   DAV2_LAUNCH_OK();
   return 0;
 }

@@ -13,7 +13,9 @@ int launch_bilinear_nhwc(const h16* in, h16* out, int B, int Hi, int Wi, int Ho,
 int launch_bilinear_f32(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
 int launch_cast_bf16(const float* in, h16* out, long long n, cudaStream_t stream);
 
-int launch_preprocess_bgr(const uint8_t* img, int H, int W, float* out, int nh, int nw, cudaStream_t stream);
+int launch_preprocess_bgr(const uint8_t* img, int B, int H, int W, float* out, int nh, int nw, cudaStream_t stream);
+int launch_resample_aa(int mode, const void* in, int B, int H, int W, float* out, int Ho, int Wo, float div_in,
+                       cudaStream_t stream);
 
 // voxel.cu
 int launch_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* valid, long long n, double voxel, float* out_xyz,

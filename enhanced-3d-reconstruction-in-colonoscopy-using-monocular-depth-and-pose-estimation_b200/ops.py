@@ -267,11 +267,39 @@ def compose_poses(rel: torch.Tensor, init7: torch.Tensor | None = None, want_T12
 
 
 def preprocess_bgr_u8(img_u8: torch.Tensor, nh: int, nw: int) -> torch.Tensor:
-    """BGR uint8 [H,W,3] (device) -> normalised RGB fp32 [1,3,nh,nw] with OpenCV-compatible bicubic resize."""
+    """BGR uint8 [H,W,3] or [B,H,W,3] (device) -> normalised RGB fp32 [B,3,nh,nw] with OpenCV-compatible bicubic resize
+    (upstream image2tensor; one launch for the whole batch)."""
     require_cuda(img_u8, "img")
-    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3
-    H, W = img_u8.shape[:2]
-    out = torch.empty(1, 3, nh, nw, dtype=torch.float32, device=img_u8.device)
-    check(_lib.load().dav2_preprocess_bgr_u8(img_u8.data_ptr(), H, W, out.data_ptr(), nh, nw,
-                                             current_stream_ptr(img_u8.device)), "dav2_preprocess_bgr_u8")
+    if img_u8.dim() == 3:
+        img_u8 = img_u8[None]
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
+    B, H, W = img_u8.shape[:3]
+    out = torch.empty(B, 3, nh, nw, dtype=torch.float32, device=img_u8.device)
+    check(_lib.load().dav2_preprocess_bgr_u8_batch(img_u8.data_ptr(), B, H, W, out.data_ptr(), nh, nw,
+                                                   current_stream_ptr(img_u8.device)), "dav2_preprocess_bgr_u8_batch")
+    return out
+
+
+def resize_aa(x: torch.Tensor, Ho: int, Wo: int, div_in: float | None = None) -> torch.Tensor:
+    """torch's anti-aliased bicubic ``Resize((Ho, Wo), BICUBIC, antialias=True)`` after ToTensor, on the GPU (dav2_resize_aa).
+
+    uint8 [B,H,W,3] RGB -> /255 -> resize -> ImageNet normalisation -> fp32 [B,3,Ho,Wo]   (SimCol transform_input)
+    uint16 / float32 [B,H,W] -> / div_in (default 65535 for uint16, 1 for float) -> resize -> fp32 [B,1,Ho,Wo]
+    (SimCol transform_output)."""
+    require_cuda(x, "x")
+    if x.dtype == torch.uint8:
+        assert x.dim() == 4 and x.shape[3] == 3, "uint8 input must be [B,H,W,3] RGB"
+        mode, C, s = 0, 3, (255.0 if div_in is None else div_in)
+    elif x.dtype == torch.uint16:
+        assert x.dim() == 3, "uint16 input must be [B,H,W]"
+        mode, C, s = 1, 1, (65535.0 if div_in is None else div_in)
+    elif x.dtype == torch.float32:
+        assert x.dim() == 3, "float32 input must be [B,H,W]"
+        mode, C, s = 2, 1, (1.0 if div_in is None else div_in)
+    else:
+        raise _lib.Dav2Error(f"resize_aa: unsupported dtype {x.dtype}")
+    B, H, W = x.shape[:3]
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
+    check(_lib.load().dav2_resize_aa(mode, x.data_ptr(), B, H, W, out.data_ptr(), Ho, Wo, float(s), current_stream_ptr(x.device)),
+          "dav2_resize_aa")
     return out

@@ -69,18 +69,18 @@ def run_frames(model, filenames: Iterable[str], outdir: str, input_size: int = 5
     for s in range(0, len(todo), batch):
         names = todo[s:s + batch]
         raws = [cv2.imread(f) for f in names]
-        tens = [model.image2tensor(r, input_size) for r in raws]
-        # batch frames that share a network input shape; others run alone (infer_image semantics per frame)
+        # frames of equal size share ONE upload of the uint8 batch, one pre-processing launch (OpenCV-compatible bicubic +
+        # normalisation on the GPU, upstream image2tensor), one forward and one resize back (infer_image semantics per frame)
         groups = {}
-        for i, (t, hw) in enumerate(tens):
-            groups.setdefault(tuple(t.shape[-2:]), []).append(i)
+        for i, r in enumerate(raws):
+            groups.setdefault(tuple(r.shape[:2]), []).append(i)
         depths = [None] * len(names)
-        for shape, idxs in groups.items():
-            x = torch.cat([tens[i][0] for i in idxs]).to(dev)
-            d = model(x)
+        for (h, w), idxs in groups.items():
+            nh, nw = model.target_size(h, w, input_size)
+            u8 = torch.from_numpy(np.stack([raws[i] for i in idxs])).to(dev, non_blocking=True)
+            d = ops.resize_depth(model(ops.preprocess_bgr_u8(u8, nh, nw)), h, w).cpu().numpy()
             for j, i in enumerate(idxs):
-                h, w = tens[i][1]
-                depths[i] = ops.resize_depth(d[j:j + 1].contiguous(), h, w)[0].cpu().numpy()
+                depths[i] = d[j]
         for name, raw, depth in zip(names, raws, depths):
             stem = os.path.join(outdir, os.path.splitext(os.path.basename(name))[0])
             if save_numpy:

@@ -88,6 +88,21 @@ int dav2_resize_depth(const float* in, int32_t B, int32_t Hi, int32_t Wi, float*
  * normalisation -> out device fp32 [3,nh,nw].  (nh, nw) = the lower-bound, multiple-of-14 size computed by the host. */
 int dav2_preprocess_bgr_u8(const uint8_t* img, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw, void* stream);
 
+/* The same for a batch of equally sized frames (the run.py frame loop in batches): img device u8 [B,H,W,3] BGR ->
+ * out device fp32 [B,3,nh,nw]. */
+int dav2_preprocess_bgr_u8_batch(const uint8_t* img, int32_t B, int32_t H, int32_t W, float* out, int32_t nh, int32_t nw,
+                                 void* stream);
+
+/* Dataset pre-processing of the SimCol loader (data_processing/simcol.py:104-135 transform_input / transform_output,
+ * :161-168 __getitem__): ToTensor -> transforms.Resize((Ho, Wo), BICUBIC, antialias=True) [-> Normalize], i.e. torch's
+ * anti-aliased bicubic (a = -0.5, taps renormalised at the borders, kernel widened by the scale when down-sampling).
+ * Inputs are divided by div_in (IEEE division, like `image.astype(np.float32) / 255.0`) before the resampling.
+ *   mode 0: in device u8  [B,H,W,3] RGB (PIL order) / div_in (255) -> resize -> ImageNet normalisation -> out fp32 [B,3,Ho,Wo]
+ *   mode 1: in device u16 [B,H,W] / div_in (65535) -> resize                                        -> out fp32 [B,1,Ho,Wo]
+ *   mode 2: in device fp32 [B,H,W] / div_in -> resize                                               -> out fp32 [B,1,Ho,Wo] */
+int dav2_resize_aa(int32_t mode, const void* in, int32_t B, int32_t H, int32_t W, float* out, int32_t Ho, int32_t Wo,
+                   float div_in, void* stream);
+
 /* Fused back-projection + SE(3) world transform + validity mask.
  * Replaces depth_to_pointcloud.py:218-239 (Open3D RGBD -> PointCloud.create_from_rgbd_image -> transform)
  * and the explicit formula at depth_to_pointcloud_dav2.py:300-313.
