@@ -409,7 +409,9 @@ __device__ __forceinline__ AaAxis aa_axis(int i, int in, float scale) {
   AaAxis ax;
   const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
   ax.inv = scale >= 1.0f ? 1.0f / scale : 1.0f;
-  ax.center = scale * ((float)i + 0.5f);
+  // __fmul_rn: the product must be ROUNDED to fp32 like ATen's `center`; left to the compiler, `tap - scale * (i + 0.5)` is
+  // contracted into one FMA with an unrounded product -- half an ulp of 474 = 1.5e-5 in every weight argument
+  ax.center = __fmul_rn(scale, (float)i + 0.5f);
   ax.lo = max((int)(ax.center - support + 0.5f), 0);
   ax.n = min((int)(ax.center + support + 0.5f), in) - ax.lo;
   float t = 0.f;

@@ -8,6 +8,8 @@
 //                       finalised on the host AFTER any cross-GPU all-reduce.  8 B/px.
 //  compose_poses_kernel the strictly sequential fp32 pose chain of eval/evaluation.py:279-382
 //                       (+ quaternion -> [R|t] rows in fp64, depth_to_pointcloud.py:168-173).
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 
 namespace dav2 {
@@ -47,7 +49,7 @@ struct BpFrame {
 };
 
 __device__ __forceinline__ void bp_frame_setup(BpFrame& fs, int c, const double* K, const double* T12, int b, int W,
-                                               double inv_scale, double trunc) {
+                                               double inv_scale, float d_thr) {
   // x = (u-cx)/fx * z: the oracle divides; 1/fx in fp64 then multiplies differs by <= 1 ulp(fp64)
   const double fx_inv = 1.0 / K[0], fy_inv = 1.0 / K[1], cx = K[2], cy = K[3];
   const bool hasT = T12 != nullptr;
@@ -60,43 +62,43 @@ __device__ __forceinline__ void bp_frame_setup(BpFrame& fs, int c, const double*
   fs.t[c] = hasT ? T12[12 * b + 4 * c + 3] : 0.0;
   if (c == 0) {
     fs.inv_scale = inv_scale;
-    float thr = INFINITY;
-    if (trunc < (double)INFINITY) {  // smallest float whose z = (double)d * inv_scale is >= trunc
-      thr = (float)(trunc / inv_scale);
-      for (int i = 0; i < 4 && (double)thr * inv_scale < trunc; ++i) thr = nextafterf(thr, INFINITY);
-      for (int i = 0; i < 4 && (double)nextafterf(thr, -INFINITY) * inv_scale >= trunc; ++i) thr = nextafterf(thr, -INFINITY);
-    }
-    fs.d_thr = thr;
+    fs.d_thr = d_thr;
   }
 }
 
-// select without a branch: the compiler otherwise sinks the three DFMA + F2F of a pixel under `if (ok)` and pays
-// BSSY / BRA / BSYNC + zero-initialisation per pixel although nearly every pixel is valid
-__device__ __forceinline__ float sel_or_zero(float v, bool ok) {
-  float r;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tselp.f32 %0, %1, 0f00000000, p;\n\t}" : "=f"(r) : "f"(v), "r"((unsigned)ok));
-  return r;
+// smallest float d whose z = (double)d * inv_scale reaches depth_trunc (host side: a function of two launch scalars)
+static float depth_threshold(double inv_scale, double trunc) {
+  if (!(trunc < (double)INFINITY)) return INFINITY;
+  float thr = (float)(trunc / inv_scale);
+  for (int i = 0; i < 4 && (double)thr * inv_scale < trunc; ++i) thr = nextafterf(thr, INFINITY);
+  for (int i = 0; i < 4 && (double)nextafterf(thr, -INFINITY) * inv_scale >= trunc; ++i) thr = nextafterf(thr, -INFINITY);
+  return thr;
 }
 
-__device__ __forceinline__ bool backproject_one(float d, const double (&ray)[3], const BpFrame& f, float& X, float& Y, float& Z) {
-  const bool ok = (d > 0.f) && (d < f.d_thr);  // NaN fails both; +-inf fails one of them
+// One pixel: returns an all-ones / all-zero validity mask; the outputs are AND-ed with it (a `cond ? v : 0` select made
+// the compiler sink the three DFMA + F2F of a pixel under a branch: BSSY / BRA / BSYNC + zero-initialisation per pixel
+// although nearly every pixel is valid).
+__device__ __forceinline__ unsigned backproject_one(float d, const double (&ray)[3], const BpFrame& f, float& X, float& Y, float& Z) {
+  const unsigned mk = ((d > 0.f) && (d < f.d_thr)) ? 0xffffffffu : 0u;  // NaN fails both tests; +-inf fails one of them
   const double z = (double)d * f.inv_scale;
-  X = sel_or_zero((float)fma(z, ray[0], f.t[0]), ok);
-  Y = sel_or_zero((float)fma(z, ray[1], f.t[1]), ok);
-  Z = sel_or_zero((float)fma(z, ray[2], f.t[2]), ok);
-  return ok;
+  X = __uint_as_float(__float_as_uint((float)fma(z, ray[0], f.t[0])) & mk);
+  Y = __uint_as_float(__float_as_uint((float)fma(z, ray[1], f.t[1])) & mk);
+  Z = __uint_as_float(__float_as_uint((float)fma(z, ray[2], f.t[2])) & mk);
+  return mk;
 }
 
-// 4 consecutive pixels starting at linear index p0 (row-major); returns the number of valid ones.
-// CROSS = false: the caller knows that no quad of the warp straddles two image rows (7 of 8 warps at W = 518).
+// 4 consecutive pixels starting at linear index p0 (row-major); m = validity bytes (uchar4 of 0 / 1), returns their count.
+// CROSS = false: the caller knows that no quad of the warp straddles two image rows (7 of 8 warps at W = 518); otherwise
+// pixels k >= W - u are on row v + 1 (at most one row change: W >= 4).  (An out-of-line CROSS path made the compiler keep
+// o[] in local memory for every quad: 58 -> 93 us.)
 template <bool CROSS>
 __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, int W, unsigned wmagic, const BpFrame& f,
-                                                float (&o)[12], uchar4& m) {
+                                                float (&o)[12], unsigned& m) {
   // v = p0 / W: multiply-high by ceil(2^32 / W) is exact while p0 * W < 2^32 (the launcher sends larger frames to the
   // scalar kernel)
   const unsigned v = __umulhi(p0, wmagic);
   const int u = (int)(p0 - v * (unsigned)W);
-  const int nrow = W - u;  // pixels k >= nrow of the quad are on row v + 1 (at most one row change: W >= 4)
+  const int nrow = W - u;
   const double ud = (double)u, vd = (double)(int)v;
   double ra[3], rb[3];
 #pragma unroll
@@ -105,8 +107,7 @@ __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, in
     if (CROSS) rb[c] = ra[c] + f.wrap[c];
   }
   const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-  uint8_t* mm = &m.x;
-  int nvalid = 0;
+  unsigned mk[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     double ray[3];
@@ -115,11 +116,10 @@ __device__ __forceinline__ int backproject_quad(const float4 d4, unsigned p0, in
       const double base = (!CROSS || k < nrow) ? ra[c] : rb[c];
       ray[c] = k == 0 ? base : fma((double)k, f.dx[c], base);  // (fma(0, dx, base) is not folded: dx could be inf / NaN)
     }
-    const bool ok = backproject_one(dd[k], ray, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
-    mm[k] = ok ? 1 : 0;
-    nvalid += ok ? 1 : 0;
+    mk[k] = backproject_one(dd[k], ray, f, o[3 * k], o[3 * k + 1], o[3 * k + 2]);
   }
-  return nvalid;
+  m = (mk[0] & 0x1u) | (mk[1] & 0x100u) | (mk[2] & 0x10000u) | (mk[3] & 0x1000000u);
+  return __popc(m);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -274,21 +274,22 @@ __device__ __forceinline__ void metric_block_reduce(const MetricAccF& a, double*
   }
 }
 
-// Vector path: a block owns 512 consecutive float4s (2048 pixels) of ONE frame; thread t takes quads t and t + 256, all
-// loads (depth, and gt when the metric sums ride along) in flight before any math.  Each thread's 4 points are 48
-// contiguous bytes; storing them directly makes every warp-wide store touch 12 lines with 16 of every 48 bytes (ncu:
-// 1.94x the ideal number of L2 store sectors), so the warp stages its 1536 bytes in shared memory (48-byte thread stride =
-// conflict-free for 128-bit accesses) and writes three fully coalesced 512-byte rows.
+// Vector path: a block owns QPT * 256 consecutive float4s of ONE frame; thread t takes quads t, t + 256, ...: all loads
+// (depth, and gt when the metric sums ride along) are in flight before any math, and the per-block costs (frame constants,
+// count / metric reductions, atomics) are spread over 4 * QPT pixels per thread.
+// Each thread's 4 points are 48 contiguous bytes; storing them directly makes every warp-wide store touch 12 lines with
+// 16 of every 48 bytes (ncu: 1.94x the ideal number of L2 store sectors), so the warp stages its 1536 bytes in shared
+// memory (48-byte thread stride = conflict-free for 128-bit accesses) and writes three fully coalesced 512-byte rows.
 // MULTI = false: one destination (dst.*[0]); a destination loop over a runtime count kept eight sets of predicated 64-bit
 // address arithmetic alive in the single-destination kernel as well.
 // METRICS = true (round 2): the test_step metric partial sums (variant 0: lo <= gt <= hi, eval/evaluation.py:16-60) are
 // accumulated from the SAME depth registers -- the separate metric kernel re-read the 68.7 MB depth map the head conv had
 // just written (8 B/px of its own traffic); fused, one pass moves 21 B/px instead of 17 + 8.
-template <bool MULTI, bool METRICS>
-__global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __restrict__ depth, const float* __restrict__ gt,
+template <bool MULTI, bool METRICS, int BP_QPT>
+__global__ void __launch_bounds__(256, BP_QPT == 2 ? 4 : 3) backproject_vec_kernel(const float* __restrict__ depth, const float* __restrict__ gt,
                                                                  int H, int W, unsigned wmagic, const double* __restrict__ K4,
                                                                  int k_per_frame, const double* __restrict__ T12,
-                                                                 double inv_scale, double trunc, const BpDst dst, float lo,
+                                                                 double inv_scale, float d_thr, const BpDst dst, float lo,
                                                                  float hi, int per_frame, double* __restrict__ partials) {
   const int b = blockIdx.y;
   const long long HW = (long long)H * W;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __
   // shared memory; per thread that prologue cost a third of the 8-pixel body
   __shared__ BpFrame fs;
   __shared__ float4 stage[8][96];
-  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, trunc);
+  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, d_thr);
   const float4* dfrm = reinterpret_cast<const float4*>(depth + b * HW);
   const float4* gfrm = METRICS ? reinterpret_cast<const float4*>(gt + b * HW) : nullptr;
   const long long ooff = b * HW * 3, voff = b * HW;
@@ -304,32 +305,36 @@ __global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __
   const int ndst = MULTI ? dst.n : 1;
   const unsigned nvec = (unsigned)(HW >> 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned i0 = blockIdx.x * 512u + threadIdx.x, i1 = i0 + 256u;
-  const bool h0 = i0 < nvec, h1 = i1 < nvec;
+  const unsigned i0 = blockIdx.x * (256u * BP_QPT) + threadIdx.x;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 d0 = zero, d1 = zero, g0 = zero, g1 = zero;
-  if (h0) d0 = __ldcs(dfrm + i0);
-  if (h1) d1 = __ldcs(dfrm + i1);
+  float4 dq[BP_QPT], gq[BP_QPT];
+#pragma unroll
+  for (int q = 0; q < BP_QPT; ++q) {
+    const unsigned iv = i0 + 256u * q;
+    dq[q] = iv < nvec ? __ldcs(dfrm + iv) : zero;
+  }
   if (METRICS) {
-    if (h0) g0 = __ldcs(gfrm + i0);
-    if (h1) g1 = __ldcs(gfrm + i1);
+#pragma unroll
+    for (int q = 0; q < BP_QPT; ++q) {
+      const unsigned iv = i0 + 256u * q;
+      gq[q] = iv < nvec ? __ldcs(gfrm + iv) : zero;
+    }
   }
   __syncthreads();  // frame constants; the loads above are already in flight
   int nvalid = 0;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const unsigned iv = half ? i1 : i0;
+  for (int q = 0; q < BP_QPT; ++q) {
+    const unsigned iv = i0 + 256u * q;
     const unsigned wbase = iv - lane;  // first float4 index of this warp's 32
     if (wbase >= nvec) continue;       // warp-uniform
     float o[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    uchar4 m = make_uchar4(0, 0, 0, 0);
+    unsigned m = 0u;
+    // does any quad of this warp straddle two rows?  first pixel of the warp's span: wbase*4, 128 pixels long
+    const unsigned pw = wbase * 4u;
+    const bool cross = (pw - __umulhi(pw, wmagic) * (unsigned)W) + 128u > (unsigned)W;  // warp-uniform
     if (iv < nvec) {
-      // does any quad of this warp straddle two rows?  first pixel of the warp's span: wbase*4, 128 pixels long
-      const unsigned pw = wbase * 4u;
-      const unsigned vw = __umulhi(pw, wmagic);
-      const bool cross = (pw - vw * (unsigned)W) + 128u > (unsigned)W;  // warp-uniform
-      if (cross) nvalid += backproject_quad<true>(half ? d1 : d0, iv * 4u, W, wmagic, fs, o, m);
-      else nvalid += backproject_quad<false>(half ? d1 : d0, iv * 4u, W, wmagic, fs, o, m);
+      if (cross) nvalid += backproject_quad<true>(dq[q], iv * 4u, W, wmagic, fs, o, m);
+      else nvalid += backproject_quad<false>(dq[q], iv * 4u, W, wmagic, fs, o, m);
     }
     stage[warp][3 * lane] = make_float4(o[0], o[1], o[2], o[3]);
     stage[warp][3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -343,12 +348,11 @@ __global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __
       if ((unsigned)lane < nout) __stcs(op + lane, r0);
       if ((unsigned)lane + 32u < nout) __stcs(op + lane + 32, r1);
       if ((unsigned)lane + 64u < nout) __stcs(op + lane + 64, r2);
-      if (has_valid && iv < nvec) __stcs(reinterpret_cast<uchar4*>(dst.valid[p] + voff) + iv, m);
+      if (has_valid && iv < nvec) __stcs(reinterpret_cast<unsigned*>(dst.valid[p] + voff) + iv, m);
     }
   }
   if (dst.counts[0]) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
     __shared__ int wsum[8];
     if (lane == 0) wsum[warp] = nvalid;
     __syncthreads();
@@ -361,14 +365,29 @@ __global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __
   }
   if (METRICS) {
     MetricAccF c = {0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u};
-    // zero-filled (absent) quads are invalid under the variant-0 mask as long as lo > 0; h0 / h1 guard the general case
-    const bool exact = max(h0 ? metric_exact_key<0>(d0, g0, lo, hi) : 0u, h1 ? metric_exact_key<0>(d1, g1, lo, hi) : 0u) >= 0x7f7fffffu;
-    if (!exact) {
-      if (h0) metric_quad<0, false>(c, d0, g0, lo, hi);
-      if (h1) metric_quad<0, false>(c, d1, g1, lo, hi);
+    // absent quads (beyond the frame) are skipped explicitly; does any counted pixel need the literal formula?
+    // With 0 < lo and hi < inf (launch-uniform; the test_step mask) every COUNTED gt is finite and positive by the mask
+    // itself, so only the predictions decide -- and testing uncounted ones too is harmless (1.5 instead of 6 instructions
+    // per pixel; absent quads are zero-filled: key 0xffffffff, so they are skipped here as well).
+    const bool gt_safe = lo > 0.f && hi < INFINITY;
+    unsigned key = 0u;
+#pragma unroll
+    for (int q = 0; q < BP_QPT; ++q) {
+      if (i0 + 256u * q >= nvec) continue;
+      if (gt_safe)
+        key = max(key, max(max(__float_as_uint(dq[q].x) - 1u, __float_as_uint(dq[q].y) - 1u),
+                           max(__float_as_uint(dq[q].z) - 1u, __float_as_uint(dq[q].w) - 1u)));
+      else
+        key = max(key, metric_exact_key<0>(dq[q], gq[q], lo, hi));
+    }
+    if (key < 0x7f7fffffu) {
+#pragma unroll
+      for (int q = 0; q < BP_QPT; ++q)
+        if (i0 + 256u * q < nvec) metric_quad<0, false>(c, dq[q], gq[q], lo, hi);
     } else {
-      if (h0) metric_quad<0, true>(c, d0, g0, lo, hi);
-      if (h1) metric_quad<0, true>(c, d1, g1, lo, hi);
+#pragma unroll
+      for (int q = 0; q < BP_QPT; ++q)
+        if (i0 + 256u * q < nvec) metric_quad<0, true>(c, dq[q], gq[q], lo, hi);
     }
     metric_block_reduce(c, partials + (per_frame ? 8 * b : 0));
   }
@@ -377,12 +396,12 @@ __global__ void __launch_bounds__(256, 4) backproject_vec_kernel(const float* __
 // Scalar path (frames whose pixel count is not a multiple of 4, narrower than 4 pixels, or unaligned buffers)
 __global__ void __launch_bounds__(256) backproject_scalar_kernel(const float* __restrict__ depth, int H, int W,
                                                                  const double* __restrict__ K4, int k_per_frame,
-                                                                 const double* __restrict__ T12, double inv_scale, double trunc,
+                                                                 const double* __restrict__ T12, double inv_scale, float d_thr,
                                                                  const BpDst dst) {
   const int b = blockIdx.y;
   const long long HW = (long long)H * W;
   __shared__ BpFrame fs;
-  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, trunc);
+  if (threadIdx.x < 3) bp_frame_setup(fs, threadIdx.x, K4 + (k_per_frame ? 4 * b : 0), T12, b, W, inv_scale, d_thr);
   __syncthreads();
   const BpFrame f = fs;
   const float* dfrm = depth + b * HW;
@@ -395,7 +414,7 @@ __global__ void __launch_bounds__(256) backproject_scalar_kernel(const float* __
     double ray[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) ray[c] = fma((double)u, f.dx[c], fma((double)v, f.dy[c], f.r0[c]));
-    const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z);
+    const bool ok = backproject_one(dfrm[i], ray, f, X, Y, Z) != 0u;
     for (int p = 0; p < dst.n; ++p) {
       float* ofrm = dst.xyz[p] + ooff;
       ofrm[3 * i] = X; ofrm[3 * i + 1] = Y; ofrm[3 * i + 2] = Z;
@@ -452,7 +471,7 @@ int launch_backproject_multi(const float* depth, int B, int H, int W, const doub
   }
   dst.n = n_dst;
   const double inv_scale = 1.0 / (double)depth_scale;
-  const double trunc = (double)depth_trunc;  // +inf disables truncation
+  const float d_thr = depth_threshold(inv_scale, (double)depth_trunc);  // +inf disables truncation
   if (gt && !vec) {
     // unaligned / odd-sized frames: the two passes run separately (same results)
     if (int rc = launch_depth_metrics(depth, gt, B, HW, lo, hi, 0, per_frame, partials, stream)) return rc;
@@ -461,18 +480,29 @@ int launch_backproject_multi(const float* depth, int B, int H, int W, const doub
   }
   if (gt) DAV2_CUDA_OK(cudaMemsetAsync(partials, 0, sizeof(double) * 8 * (per_frame ? B : 1), stream));
   // one trip per block: a block-stride loop with a fractional number of passes leaves most SMs idle during the last one
-  long long bx = vec ? (HW / 4 + 511) / 512 : (HW + 255) / 256;
+  int qpt = 4;  // quads per thread: 72 us (4) vs 74 us (2) for the fused pass at 64 x 518^2
+#ifdef DAV2_PROFILING_KNOBS
+  if (const char* e = getenv("DAV2_BP_QPT")) qpt = atoi(e) == 2 ? 2 : 4;
+#endif
+  long long bx = vec ? (HW / 4 + 256 * qpt - 1) / (256 * qpt) : (HW + 255) / 256;
   if (bx > 1048576) bx = 1048576;
   if (bx < 1) bx = 1;
   ProfScope ps(PC_BACKPROJECT, 0.0, (double)B * HW * ((gt ? 8.0 : 4.0) + n_dst * (valid ? 13.0 : 12.0)), stream);
   dim3 grid((unsigned)bx, (unsigned)B);
-#define DAV2_BP_GO(MULTI, MET) \
-  backproject_vec_kernel<MULTI, MET><<<grid, 256, 0, stream>>>(depth, gt, H, W, wmagic, K4, k_per_frame, T12, inv_scale, trunc, dst, lo, hi, per_frame, partials)
+#define DAV2_BP_GO(MULTI, MET)                                                                                          \
+  do {                                                                                                                 \
+    if (qpt == 4)                                                                                                      \
+      backproject_vec_kernel<MULTI, MET, 4><<<grid, 256, 0, stream>>>(depth, gt, H, W, wmagic, K4, k_per_frame, T12,    \
+                                                                     inv_scale, d_thr, dst, lo, hi, per_frame, partials); \
+    else                                                                                                               \
+      backproject_vec_kernel<MULTI, MET, 2><<<grid, 256, 0, stream>>>(depth, gt, H, W, wmagic, K4, k_per_frame, T12,    \
+                                                                     inv_scale, d_thr, dst, lo, hi, per_frame, partials); \
+  } while (0)
   if (vec && n_dst == 1 && gt) DAV2_BP_GO(false, true);
   else if (vec && n_dst == 1) DAV2_BP_GO(false, false);
   else if (vec && gt) DAV2_BP_GO(true, true);
   else if (vec) DAV2_BP_GO(true, false);
-  else backproject_scalar_kernel<<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, trunc, dst);
+  else backproject_scalar_kernel<<<grid, 256, 0, stream>>>(depth, H, W, K4, k_per_frame, T12, inv_scale, d_thr, dst);
 #undef DAV2_BP_GO
   DAV2_LAUNCH_OK();
   return 0;
