@@ -218,6 +218,9 @@ def workload_config(args, world=1, gather=None, gather_note=None):
            "l2": f"inputs re-read every step are {B * 3 * S * S * 4 / 1e6:.0f} MB and activations >10 GB, larger than the 126 MB L2"}
     if gather_note:
         cfg["gather_note"] = gather_note
+    if world > 1 and gather == "fused":
+        cfg["gather_overlap"] = ("side stream: the gather stores of step i overlap the encoder of step i+1" if not args.no_overlap
+                                 else "none (main stream)")
     return cfg
 
 
@@ -296,6 +299,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the cloud gather (N>1)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1, fused gather: keep the back-projection/gather kernel on the main stream instead of a side stream "
+                         "(where its NVLink stores overlap the next batch's encoder)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: 'fused' = the back-projection kernel stores into every rank's peer-mapped gather buffer "
                          "(sharding.CloudGather); 'nccl' = local back-projection + all_gather_into_tensor")
@@ -366,30 +372,51 @@ def main():
     part_acc = torch.zeros(8, dtype=torch.float64, device=dev)   # metric partial SUMS accumulate on the device ...
     step_no = [0]
 
-    def step(x, gt):
-        """One batch through the path.  Returns (depth, xyz, valid, counts, partials) of THIS rank's frames."""
+    # N > 1, fused gather: the back-projection kernel's NVLink stores (1.86 GB per step at N = 8: 2.4 ms) run on a SIDE stream,
+    # ordered after the depth of their own step only, so they overlap the next batch's encoder instead of sitting on the
+    # critical path (round 1: un-attributed step gap 0.7 -> 6.1 ms from N = 1 to 8).
+    main_stream = torch.cuda.current_stream(dev)
+    cloud_stream = torch.cuda.Stream(device=dev) if (fused is not None and not args.no_overlap) else main_stream
+
+    def step(x, gt, before_cloud=None):
+        """One batch through the path.  Returns (depth, xyz, valid, counts, partials, done) of THIS rank's frames; `done` is
+        an event after the step's last kernel.  `before_cloud`: event the cloud stage must wait for (its output buffers)."""
         i = step_no[0]
         step_no[0] += 1
         depth = model(x)
         xyz = valid = counts = None
+        done = torch.cuda.Event()
         if cloud:
-            _, T12 = ops.compose_poses(rel, None, want_T12=True)
-            # ONE pass over the depth map: back-projection + SE(3) + validity + the metric partial sums
-            if fused is not None:
-                # the kernel's stores ARE the all-gather (no collective in the step; CloudGather.complete() orders a reader
-                # of the whole gathered cloud after all writers)
-                xa, va, ca, part = fused.backproject(depth, k4, T12[1:], gt=gt, min_depth=1e-6, max_depth=20.0)
-                xyz, valid, counts = xa[rank * B:(rank + 1) * B], va[rank * B:(rank + 1) * B], ca[rank * B:(rank + 1) * B]
-            else:
-                xyz, valid, counts, part = ops.backproject_metrics(depth, gt, k4, T12[1:], 1e-6, 20.0, out_xyz=xyz_buf[i % 2])
-                if cloud_all is not None:
-                    dist.all_gather_into_tensor(cloud_all.view(-1), xyz.view(-1))
-                    dist.all_gather_into_tensor(mask_all.view(-1), valid.view(-1))
+            if cloud_stream is not main_stream:
+                have_depth = torch.cuda.Event()
+                have_depth.record(main_stream)
+                cloud_stream.wait_event(have_depth)
+                depth.record_stream(cloud_stream)
+            if before_cloud is not None:
+                cloud_stream.wait_event(before_cloud)
+            with torch.cuda.stream(cloud_stream):
+                _, T12 = ops.compose_poses(rel, None, want_T12=True)
+                # ONE pass over the depth map: back-projection + SE(3) + validity + the metric partial sums
+                if fused is not None:
+                    # the kernel's stores ARE the all-gather (no collective in the step; CloudGather.complete() orders a
+                    # reader of the whole gathered cloud after all writers)
+                    xa, va, ca, part = fused.backproject(depth, k4, T12[1:], gt=gt, min_depth=1e-6, max_depth=20.0)
+                    xyz, valid, counts = xa[rank * B:(rank + 1) * B], va[rank * B:(rank + 1) * B], ca[rank * B:(rank + 1) * B]
+                else:
+                    xyz, valid, counts, part = ops.backproject_metrics(depth, gt, k4, T12[1:], 1e-6, 20.0, out_xyz=xyz_buf[i % 2])
+                    if cloud_all is not None:
+                        dist.all_gather_into_tensor(cloud_all.view(-1), xyz.view(-1))
+                        dist.all_gather_into_tensor(mask_all.view(-1), valid.view(-1))
+                part_acc.add_(part)  # sums accumulate on the device, all-reduced ONCE per timed region (SURVEY 0.8)
+                done.record(cloud_stream)
         else:
+            if before_cloud is not None:
+                main_stream.wait_event(before_cloud)
             part = evaluation.metric_partials(depth[:, None], gt, 1e-6, 20.0)           # compute_errors / test_step
             ops.depth_metric_partials(depth[:, None].contiguous(), gt, 0.0, 0.0, 1, True)  # calculate_metrics per frame
-        part_acc.add_(part)  # ... and are all-reduced ONCE per timed region (sums are associative, SURVEY 0.8)
-        return depth, xyz, valid, counts, part
+            part_acc.add_(part)
+            done.record(main_stream)
+        return depth, xyz, valid, counts, part, done
 
     def barrier():
         if world > 1:
@@ -399,7 +426,8 @@ def main():
     # ---- warm-up (+ self-verification of the fused gather where the driver can see it) -----------------
     gather_verified = None
     for w in range(args.warmup):
-        depth, xyz, valid, counts, _ = step(x_dev, gt_dev)
+        depth, xyz, valid, counts, _, done = step(x_dev, gt_dev)
+        main_stream.wait_event(done)
         if w == 0 and fused is not None:
             fused.complete()  # every rank's kernel has finished writing into every buffer
             buf = (fused._step - 1) % fused.n_buffers
@@ -429,7 +457,8 @@ def main():
         torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
-        step(x_dev, gt_dev)
+        done = step(x_dev, gt_dev)[-1]
+    main_stream.wait_event(done)  # the last step's cloud stage (the side stream is in order)
     if world > 1:
         dist.all_reduce(part_acc)  # the one exchange of metric sums; also orders any reader after every rank's last kernel
     ev1.record()
@@ -463,7 +492,6 @@ def main():
     h_valid = [torch.empty(B, HW, dtype=torch.uint8).pin_memory() for _ in range(2)] if cloud else None
     h_counts = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)] if cloud else None
     up_stream, down_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream(dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     computed = [torch.cuda.Event() for _ in range(2)]
@@ -488,10 +516,10 @@ def main():
             if i + 1 < n:
                 upload(i + 1)  # overlaps with this step's compute
             main_stream.wait_event(ready[s])
-            main_stream.wait_event(downloaded[s])  # step i-2's product has left the device buffers this step overwrites
-            depth, xyz, valid, counts, part = step(dx[s], dg[s])
-            consumed[s].record(main_stream)
-            computed[s].record(main_stream)
+            # step i-2's product must have left the device buffers this step overwrites (cloud stage waits for it)
+            depth, xyz, valid, counts, part, done = step(dx[s], dg[s], before_cloud=downloaded[s])
+            consumed[s] = done   # the upload stream may overwrite dx[s] / dg[s] once the whole step has read them
+            computed[s] = done
             keep[s] = (depth, xyz, valid, counts, part)  # keep the tensors alive until their download is done
             with torch.cuda.stream(down_stream):
                 down_stream.wait_event(computed[s])

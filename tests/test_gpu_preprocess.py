@@ -68,4 +68,4 @@ def test_load_item_files(tmp_path):
     Image.fromarray(dep).save(tmp_path / "Depth_0000.png")
     item = load_item(str(tmp_path / "FrameBuffer_0000.png"), str(tmp_path / "Depth_0000.png"), SimColTransforms(70))
     assert item["image"].shape == (3, 70, 70) and item["depth"].shape == (1, 70, 70)
-    assert 0.0 <= float(item["depth"].min()) and float(item["depth"].max()) <= 1.2  # bicubic overshoot only
+    assert -0.3 <= float(item["depth"].min()) and float(item["depth"].max()) <= 1.3  # [0, 1] plus bicubic over/undershoot
