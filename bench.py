@@ -557,6 +557,26 @@ def main():
     d2h_small = 8 * 8 + (4 * B if cloud else 0)
     d2h = d2h_small + B * HW * 4 + (B * HW * 13 if cloud else 0)
 
+    # the back-projection (+ metric sums) pass alone, back to back: inside the step it runs at the power-capped clock of the
+    # dense kernels around it and is instruction-issue bound there, so the in-step figure (roofline_backproject) is reported
+    # next to this one
+    bp_alone = None
+    if cloud:
+        _, T12 = ops.compose_poses(rel, None, want_T12=True)
+        xyz_t = xyz_buf[0]
+        g2 = synth_gt(B, S, S, dev, 99 + rank)
+        d2 = model(synth_frames(B, S, S, dev, 1234 + rank))
+        for _ in range(3):
+            ops.backproject_metrics(d2, g2, k4, T12[1:], 1e-6, 20.0, out_xyz=xyz_t)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(20):
+            ops.backproject_metrics(d2, g2, k4, T12[1:], 1e-6, 20.0, out_xyz=xyz_t)
+        ev1.record()
+        torch.cuda.synchronize()
+        bp_alone = ev0.elapsed_time(ev1) / 20.0  # ms per launch incl. the two 0.3 KB memsets of each call
+        del d2, g2
+
     fused_used = fused is not None
     if fused is not None:
         fused.close()
@@ -610,6 +630,11 @@ def main():
         if bp and bp["ms"] > 0:
             out[name] = {"bound": "hbm", "achieved": bp["bytes"] / (bp["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": bp["bytes"] / (bp["ms"] * 1e-3) / 1e9 / hbm, "traffic": None}
+    if bp_alone:
+        gbs = B * HW * 21.0 / (bp_alone * 1e-3) / 1e9
+        out["roofline_backproject_alone"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                             "us_per_launch": bp_alone * 1e3, "traffic": None,
+                                             "what": "the same fused pass (21 B/px, single destination) launched 20x back to back in this run"}
     if world == 1 and not args.no_gpu_baseline:
         del x_dev, gt_dev, dx, dg
         torch.cuda.empty_cache()

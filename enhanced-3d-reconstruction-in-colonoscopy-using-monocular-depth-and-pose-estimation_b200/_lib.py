@@ -57,6 +57,7 @@ SIGNATURES = {
     "dav2_peer_close": (c_int, [c_void_p]),
     "dav2_voxel_downsample": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, C.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dav2_depth_metrics": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
+    "dav2_transform_points": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "dav2_compose_poses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dav2_pose_create": (c_int, [C.POINTER(c_void_p), c_int]),
     "dav2_pose_destroy": (None, [c_void_p]),

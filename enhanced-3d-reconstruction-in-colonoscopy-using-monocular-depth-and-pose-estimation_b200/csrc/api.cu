@@ -203,6 +203,11 @@ int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW
   return launch_depth_metrics(pred, gt, B, HW, lo, hi, variant, per_frame, partials, S(stream));
 }
 
+int dav2_transform_points(float* xyz, int64_t n, const double* T12, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return launch_transform_points(xyz, (long long)n, T12, S(stream));
+}
+
 int dav2_compose_poses(const float* rel, const float* init7, int32_t N, float* abs7, double* T12, void* stream) {
   if (int rc = require_sm100()) return rc;
   return launch_compose_poses(rel, init7, N, abs7, T12, S(stream));

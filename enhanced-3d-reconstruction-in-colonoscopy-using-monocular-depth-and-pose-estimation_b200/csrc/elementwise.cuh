@@ -35,6 +35,7 @@ int launch_backproject(const float* depth, int B, int H, int W, const double* K4
                        cudaStream_t stream);
 int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW, float lo, float hi, int variant,
                          int per_frame, double* partials, cudaStream_t stream);
+int launch_transform_points(float* xyz, long long n, const double* T12, cudaStream_t stream);
 int launch_compose_poses(const float* rel, const float* init7, int N, float* abs7, double* T12, cudaStream_t stream);
 
 }  // namespace dav2

@@ -590,6 +590,33 @@ int launch_depth_metrics(const float* pred, const float* gt, int B, long long HW
 }
 
 // ----------------------------------------------------------------------------------------------
+// rigid transform of an existing cloud: p <- R p + t in fp64, one rounding to fp32 (o3d PointCloud.transform,
+// depth_to_pointcloud.py:236-239, for clouds that are already on the device)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transform_points_kernel(float* __restrict__ xyz, long long n, const double* __restrict__ T12) {
+  __shared__ double T[12];
+  if (threadIdx.x < 12) T[threadIdx.x] = T12[threadIdx.x];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    xyz[3 * i] = (float)fma(T[0], x, fma(T[1], y, fma(T[2], z, T[3])));
+    xyz[3 * i + 1] = (float)fma(T[4], x, fma(T[5], y, fma(T[6], z, T[7])));
+    xyz[3 * i + 2] = (float)fma(T[8], x, fma(T[9], y, fma(T[10], z, T[11])));
+  }
+}
+
+int launch_transform_points(float* xyz, long long n, const double* T12, cudaStream_t stream) {
+  DAV2_CHECK(xyz && T12 && n >= 0, "transform_points: null pointer");
+  if (n == 0) return 0;
+  long long bx = (n + 255) / 256;
+  if (bx > 148 * 16) bx = 148 * 16;
+  ProfScope ps(PC_OTHER, 0.0, (double)n * 24.0, stream);
+  transform_points_kernel<<<(unsigned)bx, 256, 0, stream>>>(xyz, n, T12);
+  DAV2_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // pose chain: q_{i+1} = q_i (x) r_i ; t_{i+1} = t_i + rot(q_i, tau_i); fp32, sequential, un-fused
 // (intrinsics keep nvcc from contracting mul+add into FMA so the rounding sequence matches eager torch).
 // ----------------------------------------------------------------------------------------------

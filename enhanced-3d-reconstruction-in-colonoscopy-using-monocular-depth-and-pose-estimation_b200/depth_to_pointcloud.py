@@ -86,9 +86,8 @@ class PointCloud:
 
     def transform(self, T):
         p, _ = self._cat()
-        if p is not None:
-            T = torch.as_tensor(np.asarray(T), dtype=torch.float64, device=p.device)
-            self._p = [(p.double() @ T[:3, :3].T + T[:3, 3]).float()]
+        if p is not None and p.shape[0]:
+            self._p = [ops.transform_points_(p.contiguous(), np.asarray(T, dtype=np.float64)[:3, :4])]  # fp64 math, one rounding
         return self
 
 

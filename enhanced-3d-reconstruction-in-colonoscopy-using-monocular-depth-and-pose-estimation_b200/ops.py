@@ -252,6 +252,16 @@ def depth_metric_partials(pred: torch.Tensor, gt: torch.Tensor, lo: float, hi: f
     return out
 
 
+def transform_points_(xyz: torch.Tensor, T) -> torch.Tensor:
+    """In place p <- R p + t for xyz fp32 [n,3] on the GPU; T = 4x4 (or 3x4 / 12) row-major [R|t], evaluated in fp64."""
+    require_cuda(xyz, "xyz")
+    assert xyz.dtype == torch.float32 and xyz.dim() == 2 and xyz.shape[1] == 3
+    T12 = torch.as_tensor(T, dtype=torch.float64).reshape(-1)[:12].to(xyz.device).contiguous()
+    check(_lib.load().dav2_transform_points(xyz.data_ptr(), xyz.shape[0], T12.data_ptr(), current_stream_ptr(xyz.device)),
+          "dav2_transform_points")
+    return xyz
+
+
 def compose_poses(rel: torch.Tensor, init7: torch.Tensor | None = None, want_T12: bool = False):
     require_cuda(rel, "rel")
     assert rel.dtype == torch.float32 and rel.dim() == 2 and rel.shape[1] == 7

@@ -175,6 +175,10 @@ int dav2_voxel_downsample(const float* xyz, const float* rgb, const uint8_t* val
 int dav2_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float lo, float hi,
                        int32_t variant, int32_t per_frame, double* partials, void* stream);
 
+/* o3d PointCloud.transform(T) (depth_to_pointcloud.py:236-239) for a cloud already on the device: xyz device fp32 [n,3],
+ * in place, p <- R p + t evaluated in fp64 with one rounding; T12 device fp64 [12] = rows of [R|t]. */
+int dav2_transform_points(float* xyz, int64_t n, const double* T12, void* stream);
+
 /* evaluation.compose_poses (eval/evaluation.py:279-382): rel device fp32 [N,7] (t | q xyzw),
  * init7 device fp32 [7] or NULL (identity) -> abs7 device fp32 [N+1,7]; optional T12 device fp64
  * [N+1,12] = rows of [R|t] with R = Rotation.from_quat(q).as_matrix() (depth_to_pointcloud.py:168-173). */

@@ -206,6 +206,11 @@ def test_point_cloud_api(tmp_path, golden_dir):
     assert len(pc) == int(rv.sum())
     assert _rel_err_points(pc.points, ref[rv]).max() < POINT_RTOL
     np.testing.assert_allclose(pc.colors, color.reshape(-1, 3)[rv] / 255.0, atol=1e-6)
+    # PointCloud.transform (o3d semantics, in place, returns self): fp64 on the device
+    T2 = geo.make_transform([0.5, -0.25, 2.0], [0.3, -0.1, 0.2, 0.9])
+    moved = d2p.PointCloud(pc.points_tensor.clone()).transform(T2)
+    want_pts = pc.points @ T2[:3, :3].T + T2[:3, 3]
+    assert _rel_err_points(moved.points, want_pts).max() < POINT_RTOL
     both = d2p.PointCloud()
     both += pc
     both += pc
