@@ -50,6 +50,16 @@ if what in ("conv", "all"):
         if what == "conv":
             ops.conv3x3_h16(x1, w1, bias, x1, x1, 0, want_relu=True)  # RCU conv2: two skip adds + dual output
         ops.conv3x3_h16(x2, w2, bias2, None, None, 0)   # output_conv1 at 296^2, 256 -> 128
+if what == "attn5477":  # BASELINE config 5: 16 frames of 1036^2 -> 5477 tokens per image
+    qkv5 = rnd(16 * 5477, 3 * D, scale=float(os.environ.get("DAV2_QKV_SCALE", "1.0")))
+    for _ in range(reps):
+        ops.attention_h16(qkv5, 16, 5477, D)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5): ops.attention_h16(qkv5, 16, 5477, D)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("attention 16 x 5477 tokens: %.3f ms  %.0f TFLOP/s" % (ms, 4 * 16 * 16 * 5477 * 5477 * 64 / ms / 1e9))
 if what in ("attn", "all", "attntrace"):
     qkv = rnd(M, 3 * D, scale=float(os.environ.get("DAV2_QKV_SCALE", "1.0")))
     for _ in range(reps):
