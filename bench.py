@@ -634,7 +634,9 @@ def main():
         gbs = B * HW * 21.0 / (bp_alone * 1e-3) / 1e9
         out["roofline_backproject_alone"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                              "us_per_launch": bp_alone * 1e3, "traffic": None,
-                                             "what": "the same fused pass (21 B/px, single destination) launched 20x back to back in this run"}
+                                             "what": "the same fused pass (21 B/px, single destination) launched 20x back to back right after the timed steps "
+                                                     "(the SM clock is still at the power-capped level of the step; at free clocks the "
+                                                     "kernel takes 72 us = 0.78, profiles/README.md)"}
     if world == 1 and not args.no_gpu_baseline:
         del x_dev, gt_dev, dx, dg
         torch.cuda.empty_cache()

@@ -249,9 +249,9 @@ __device__ __forceinline__ void metric_block_reduce(const MetricAcc& a, double* 
     atomicAdd(dst + threadIdx.x, s);
   }
 }
-// fp32 inputs (the fused kernel: 8 pixels per thread): the warp's 256 pixels are summed with fp32 shuffles (20 SHFL +
-// 20 FADD per thread instead of 40 + 20 DADD -- the fp64 butterfly was a fifth of the fused kernel's instructions), the
-// eight warp sums and everything after them stay fp64.  256 terms in fp32: <= 2e-6 relative on a warp sum, random in sign.
+// fp32 inputs (the fused kernel: 4 * QPT pixels per thread): the warp's 512 pixels are summed with fp32 shuffles (20 SHFL
+// + 20 FADD per thread instead of 40 + 20 DADD -- the fp64 butterfly was a fifth of the fused kernel's instructions), the
+// eight warp sums and everything after them stay fp64.  512 terms in fp32: <= 2e-6 relative on a warp sum, random in sign.
 __device__ __forceinline__ void metric_block_reduce(const MetricAccF& a, double* __restrict__ dst) {
   float v[4] = {a.s_abs, a.s_rel, a.s_sq, a.s_gt};
 #pragma unroll
@@ -276,7 +276,10 @@ __device__ __forceinline__ void metric_block_reduce(const MetricAccF& a, double*
 
 // Vector path: a block owns QPT * 256 consecutive float4s of ONE frame; thread t takes quads t, t + 256, ...: all loads
 // (depth, and gt when the metric sums ride along) are in flight before any math, and the per-block costs (frame constants,
-// count / metric reductions, atomics) are spread over 4 * QPT pixels per thread.
+// count / metric reductions, atomics) are spread over 4 * QPT pixels per thread.  (A persistent variant -- one resident
+// wave, each block walking ~20 tiles of its frame with the next tile's loads issued before the current tile's math -- was
+// built and measured in round 2: 62 / 74 us instead of 53 / 72, and the same 97 us inside the step: the kernel is bound by
+// the core clock it gets, not by exposed load latency.)
 // Each thread's 4 points are 48 contiguous bytes; storing them directly makes every warp-wide store touch 12 lines with
 // 16 of every 48 bytes (ncu: 1.94x the ideal number of L2 store sectors), so the warp stages its 1536 bytes in shared
 // memory (48-byte thread stride = conflict-free for 128-bit accesses) and writes three fully coalesced 512-byte rows.
