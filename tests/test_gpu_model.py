@@ -102,7 +102,8 @@ def test_full_size_batch_properties_vitl():
     """BASELINE configs[2] at its real size (vitl, 64 frames of 518^2 -- too large for the CPU oracle): size-independent
     properties instead.  (1) frames are independent: frames 0 / 31 / 63 of the batch equal the same frames run alone to
     16-bit rounding noise; (2) permuting the batch permutes the output; (3) the fp32 engine agrees on one frame at its
-    own 1e-4 gate x the fp16 gate; (4) the output is finite, inside (0, max_depth) and non-degenerate."""
+    own 1e-4 gate x the fp16 gate; (4) the output is finite, inside (0, max_depth) and non-degenerate; (5) frames 0 and 63
+    OF THE 64-FRAME BATCH match the CPU oracle run on them alone (the oracle needs ~4 s per vitl frame)."""
     from dav2_b200 import weights
     from dav2_b200.dpt import MODEL_CONFIGS, DepthAnythingV2
     m = DepthAnythingV2(**MODEL_CONFIGS["vitl"], max_depth=20.0)
@@ -119,6 +120,14 @@ def test_full_size_batch_properties_vitl():
     perm = torch.arange(63, -1, -1, device="cuda")
     flipped = m(x[perm].contiguous())
     assert float((flipped[perm] - whole).abs().max() / whole.abs().max()) < DEPTH_TOL
+    # (5) and against the CPU oracle itself on the first and last frame of the 64-frame batch (same weights)
+    oracle = O.DepthAnythingV2("vitl", 256, [256, 512, 1024, 1024], max_depth=20.0).eval()
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        for b in (0, 63):
+            ref_b = oracle(x[b:b + 1].cpu())[0]
+            err = (whole[b].cpu() - ref_b).abs()
+            assert float(err.max() / ref_b.abs().max()) < DEPTH_TOL and float(err.mean() / ref_b.abs().mean()) < DEPTH_TOL, b
     m32 = DepthAnythingV2(**MODEL_CONFIGS["vitl"], max_depth=20.0, precision="fp32")
     m32.load_state_dict(m.state_dict())
     m32 = m32.cuda().eval()
