@@ -192,7 +192,8 @@ class ProcedureMetricCollector:
     def on_test_batch_end(self, outputs: dict, batch: dict):
         if not all(k in outputs for k in self.KEYS):
             raise ValueError("Missing expected keys in outputs")
-        m = {k: float(outputs[k]) for k in self.KEYS}
+        vals = torch.stack([torch.as_tensor(outputs[k]).detach().to(torch.float64).reshape(()) for k in self.KEYS])
+        m = dict(zip(self.KEYS, vals.tolist()))  # one device read per batch
         for ds, fid in zip(batch["dataset"], batch["id"]):
             p = self.procedure_of(str(ds), str(fid))
             if p is not None:

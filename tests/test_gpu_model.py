@@ -164,3 +164,45 @@ def test_cpu_input_is_rejected():
     _, m = _build("vits")
     with pytest.raises(Dav2Error):
         m(O.synthetic_frames(1, 70, 70))
+
+
+def test_lightning_module_test_and_predict():
+    """lightning_model.DepthAnythingV2Module.test_step / predict_step (lightning_model.py:289-330, :343-360) driven by
+    the trainer.test mirror with the per-procedure collector (test_lightning.py:47-111): per-batch metrics equal the
+    oracle's mask + compute_errors on the module's own prediction, the logged epoch means are the means over batches,
+    and the prediction itself is the oracle's depth."""
+    from oracle import metrics_oracle as MO
+    from dav2_b200 import lightning_model as lm
+    from dav2_b200.evaluation import ProcedureMetricCollector
+    oracle = O.build_oracle("vits", seed=0)
+    mod = lm.DepthAnythingV2Module(encoder="vits", min_depth=1e-6, max_depth=20.0)
+    mod.load_state_dict({f"model.{k}": v for k, v in oracle.state_dict().items()})
+    mod = mod.cuda().eval()
+    assert mod.device.type == "cuda"
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for i, B in enumerate((3, 2)):
+        x = O.synthetic_frames(B, 70, 98, seed=20 + i)
+        gt = (torch.rand(B, 1, 70, 98, generator=g) * 25.0)          # some above max_depth = 20 -> masked out
+        gt[torch.rand(B, 1, 70, 98, generator=g) < 0.05] = 0.0       # and some invalid zeros
+        batches.append({"image": x, "depth": gt, "dataset": ["data/SyntheticColon_I"] * B,
+                        "id": [f"S{i + 1}_{j:04d}" for j in range(B)]})
+    coll = ProcedureMetricCollector()
+    logged = lm.test(mod, batches, callbacks=[coll])
+    preds = lm.predict(mod, batches)
+    per_batch = []
+    for b, p in zip(batches, preds):
+        assert p.shape == (b["image"].shape[0], 70, 98) and p.is_cuda
+        with torch.no_grad():
+            ref = oracle(b["image"])
+        assert float((p.cpu() - ref).abs().max() / ref.abs().max()) < DEPTH_TOL
+        per_batch.append(MO.test_step_metrics(p.cpu().numpy()[:, None], b["depth"].numpy(), 1e-6, 20.0))
+    for k in ("d1", "abs_rel", "rmse", "l1"):
+        want = float(np.mean([m[k] for m in per_batch]))
+        assert abs(logged[f"Test/test_{k}"] - want) <= 1e-4 * max(abs(want), 1e-6), (k, logged, want)
+    s = coll.summary()["per_procedure"]
+    assert set(s) == {"SyntheticColon_I/Frames_S1", "SyntheticColon_I/Frames_S2"}
+    assert len(coll.metrics_by_procedure["SyntheticColon_I/Frames_S1"]) == 3
+    for i, name in enumerate(("SyntheticColon_I/Frames_S1", "SyntheticColon_I/Frames_S2")):
+        for k in ("d1", "abs_rel", "rmse", "l1"):
+            assert abs(s[name][k] - per_batch[i][k]) <= 1e-4 * max(abs(per_batch[i][k]), 1e-6)

@@ -126,3 +126,33 @@ def test_input_output_files(tmp_path):
     single = str(t / "frame_1.jpg")
     rgb, dep, out = d2p.input_output_files(NS(img_path=single, depth_path="d.png", ds_type="simcol", outdir=None))
     assert rgb == [single] and dep == [] and out == str(t)
+
+
+def test_lightning_module_surface():
+    """lightning_model.DepthAnythingV2Module mirror: constructor / hparams / checkpoint key handling run without a
+    GPU (the engine is created on first forward)."""
+    import torch
+    from dav2_b200 import lightning_model as lm
+    mod = lm.DepthAnythingV2Module(encoder="vits", min_depth=1e-6, max_depth=20.0, encoder_lr=5e-6)
+    assert mod.hparams.encoder == "vits" and mod.hparams.max_depth == 20.0 and mod.hparams.encoder_lr == 5e-6
+    assert mod.model.max_depth == 20.0 and mod.device.type == "cpu"
+    sd = mod.state_dict()
+    assert all(k.startswith("model.") for k in sd) and any("pretrained" in k for k in sd)
+    # a Lightning checkpoint's state_dict loads back (test_lightning.py:114-130); stray keys are rejected when strict
+    key = next(k for k in sd if k.endswith("cls_token"))
+    sd2 = {k: (torch.full_like(v, 0.25) if k == key else v) for k, v in sd.items()}
+    mod.load_state_dict(sd2)
+    assert float(mod.model.state_dict()[key[len("model."):]].flatten()[0]) == 0.25
+    with pytest.raises(RuntimeError):
+        mod.load_state_dict({**sd2, "loss.weight": torch.zeros(1)})
+    with pytest.raises(NotImplementedError):
+        mod.training_step({}, 0)
+    with pytest.raises(ValueError):
+        lm.DepthAnythingV2Module(encoder="vitg")
+    with pytest.raises(FileNotFoundError):
+        lm.DepthAnythingV2Module(encoder="vits", pretrained_from="/nonexistent/ckpt.pth")
+    means = lm._DeviceMeans()
+    assert all(np.isnan(v) for v in means.compute().values())
+    means.update({"d1": 0.5, "abs_rel": 1.0, "rmse": 2.0, "l1": 3.0})
+    means.update({"d1": torch.tensor(1.0), "abs_rel": torch.tensor(3.0), "rmse": torch.tensor(4.0), "l1": torch.tensor(5.0)})
+    assert means.compute() == {"d1": 0.75, "abs_rel": 2.0, "rmse": 3.0, "l1": 4.0}
