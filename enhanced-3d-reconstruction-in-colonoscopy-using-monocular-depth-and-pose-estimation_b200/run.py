@@ -57,6 +57,26 @@ def output_path(filename: str, outdir: str) -> str:
 
 
 @torch.no_grad()
+def infer_images(model, raws: List[np.ndarray], input_size=518, device=None) -> List[torch.Tensor]:
+    """``infer_image`` for a list of BGR uint8 frames, batched: frames of equal size share ONE upload of the uint8
+    batch, one pre-processing launch (OpenCV-compatible bicubic + normalisation on the GPU, upstream image2tensor), one
+    forward and one resize back.  ``input_size=None`` means "the frame's own height", the way
+    depth_to_pointcloud_dav2.py:291 calls it.  Returns per-frame device tensors [h,w] in input order."""
+    dev = device if device is not None else next(model.parameters()).device
+    groups = {}
+    for i, r in enumerate(raws):
+        groups.setdefault(tuple(r.shape[:2]), []).append(i)
+    depths = [None] * len(raws)
+    for (h, w), idxs in groups.items():
+        nh, nw = model.target_size(h, w, h if input_size is None else input_size)
+        u8 = torch.from_numpy(np.stack([raws[i] for i in idxs])).to(dev, non_blocking=True)
+        d = ops.resize_depth(model(ops.preprocess_bgr_u8(u8, nh, nw)), h, w)
+        for j, i in enumerate(idxs):
+            depths[i] = d[j]
+    return depths
+
+
+@torch.no_grad()
 def run_frames(model, filenames: Iterable[str], outdir: str, input_size: int = 518, save_numpy: bool = False,
                pred_only: bool = True, grayscale: bool = True, batch: int = 16, skip_existing: bool = True) -> List[str]:
     """Process image files like the run.py loop; returns the list of written PNG paths."""
@@ -69,18 +89,7 @@ def run_frames(model, filenames: Iterable[str], outdir: str, input_size: int = 5
     for s in range(0, len(todo), batch):
         names = todo[s:s + batch]
         raws = [cv2.imread(f) for f in names]
-        # frames of equal size share ONE upload of the uint8 batch, one pre-processing launch (OpenCV-compatible bicubic +
-        # normalisation on the GPU, upstream image2tensor), one forward and one resize back (infer_image semantics per frame)
-        groups = {}
-        for i, r in enumerate(raws):
-            groups.setdefault(tuple(r.shape[:2]), []).append(i)
-        depths = [None] * len(names)
-        for (h, w), idxs in groups.items():
-            nh, nw = model.target_size(h, w, input_size)
-            u8 = torch.from_numpy(np.stack([raws[i] for i in idxs])).to(dev, non_blocking=True)
-            d = ops.resize_depth(model(ops.preprocess_bgr_u8(u8, nh, nw)), h, w).cpu().numpy()
-            for j, i in enumerate(idxs):
-                depths[i] = d[j]
+        depths = [d.cpu().numpy() for d in infer_images(model, raws, input_size, dev)]
         for name, raw, depth in zip(names, raws, depths):
             stem = os.path.join(outdir, os.path.splitext(os.path.basename(name))[0])
             if save_numpy:

@@ -169,3 +169,45 @@ def test_config1_fixture_frame(golden_dir):
     full, _ = geo.backproject(ref, tuple(g["k4"]), np.eye(4))
     rel_full = np.linalg.norm(xyz[0].cpu().numpy() - full, axis=1) / np.linalg.norm(full, axis=1)
     assert rel_full.max() < 1e-5
+
+
+def _read_ply(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    head, body = raw.split(b"end_header\n", 1)
+    n = int([l for l in head.decode().splitlines() if l.startswith("element vertex")][0].split()[-1])
+    rec = np.frombuffer(body, dtype=[("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("r", "u1"), ("g", "u1"), ("b", "u1")], count=n)
+    return np.stack([rec["x"], rec["y"], rec["z"]], 1), np.stack([rec["r"], rec["g"], rec["b"]], 1)
+
+
+def test_pointcloud_dav2_frame_loop(golden_dir, tmp_path):
+    """depth_to_pointcloud_dav2.py:247-326 end to end on the reference's frame and a second frame of another size:
+    infer_image(image, height) -> every pixel back-projected with the cam file's K -> PLY.  Depth against the oracle's
+    infer_image, points against the script's fp64 numpy formula on that depth, colours = the file's RGB."""
+    import cv2
+    from dav2_b200 import depth_to_pointcloud_dav2 as pc
+    crop = cv2.imread(os.path.join(golden_dir, "FrameBuffer_0051_left475.png"))
+    cv2.imwrite(str(tmp_path / "frame_a.png"), crop)
+    cv2.imwrite(str(tmp_path / "frame_b.png"), crop[100:324, 50:386])   # 224 x 336
+    cv2.imwrite(str(tmp_path / "frame_c.png"), crop[::-1].copy())       # same size as a: shares its batch
+    cam = tmp_path / "cam.txt"
+    cam.write_text("156.0432 0 178.5605 0 155.7543 181.8043 0 0 1\n")
+    oracle, m = _build("vits")
+    names = [str(tmp_path / f"frame_{c}.png") for c in "abc"]
+    out = pc.process_frames(m, names, str(tmp_path / "out"), cam_file=str(cam), batch=3)
+    assert [os.path.basename(p) for p in out] == ["frame_a.ply", "frame_b.ply", "frame_c.ply"]
+    fx, fy, cx, cy = 156.0432, 155.7543, 178.5605, 181.8043
+    for name, ply in zip(names, out):
+        img = cv2.imread(name)
+        h, w = img.shape[:2]
+        pts, cols = _read_ply(ply)
+        assert pts.shape == (h * w, 3)
+        assert np.array_equal(cols.reshape(h, w, 3), img[:, :, ::-1])
+        ref = oracle.infer_image(img, h)
+        z = pts[:, 2].reshape(h, w)
+        assert np.abs(z - ref).max() / np.abs(ref).max() < GATE
+        assert np.array_equal(z.astype(np.float32), m.infer_image(img, h))  # batched == per-frame infer_image
+        x, y = np.meshgrid(np.arange(w), np.arange(h))
+        want = np.stack(((x - cx) / fx * z, (y - cy) / fy * z, z), -1).reshape(-1, 3)
+        rel = np.linalg.norm(pts - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() < 1e-6, rel.max()

@@ -156,3 +156,54 @@ def test_lightning_module_surface():
     means.update({"d1": 0.5, "abs_rel": 1.0, "rmse": 2.0, "l1": 3.0})
     means.update({"d1": torch.tensor(1.0), "abs_rel": torch.tensor(3.0), "rmse": torch.tensor(4.0), "l1": torch.tensor(5.0)})
     assert means.compute() == {"d1": 0.75, "abs_rel": 2.0, "rmse": 3.0, "l1": 4.0}
+
+
+def test_pointcloud_dav2_host_side(tmp_path):
+    """depth_to_pointcloud_dav2.py host helpers: camera file, input listing, camera selection, pose file, checkpoint keys."""
+    import torch
+    from scipy.spatial.transform import Rotation
+    from dav2_b200 import depth_to_pointcloud_dav2 as pc
+    cam = tmp_path / "cam.txt"
+    cam.write_text("227.60416 0 227.5 0 237.5 237.5 0 0 1\nignored second line\n")
+    assert pc.read_cam_file(str(cam)) == {"fx": 227.60416, "fy": 237.5, "cx": 227.5, "cy": 237.5}
+    # listing (:189-240): txt list, single file, simcol tree without the _OP folders, testing jpgs
+    lst = tmp_path / "list.txt"
+    lst.write_text("a.png\nb.png")
+    assert pc.collect_filenames(str(lst)) == (["a.png", "b.png"], None)
+    one = tmp_path / "one.png"
+    one.write_bytes(b"")
+    assert pc.collect_filenames(str(one)) == ([str(one)], str(tmp_path))
+    assert pc.collect_filenames(str(one), outdir="o") == ([str(one)], "o")
+    root = tmp_path / "SyntheticColon"
+    for d in ("SyntheticColon_I/Frames_S1", "SyntheticColon_I/Frames_S1_OP", "SyntheticColon_III/Frames_O2"):
+        (root / d).mkdir(parents=True)
+        (root / d / "FrameBuffer_0000.png").write_bytes(b"")
+        (root / d / "Depth_0000.png").write_bytes(b"")
+    files, outdir = pc.collect_filenames(str(root), "simcol")
+    assert outdir == str(root) and sorted(os.path.relpath(f, root) for f in files) == [
+        "SyntheticColon_I/Frames_S1/FrameBuffer_0000.png", "SyntheticColon_III/Frames_O2/FrameBuffer_0000.png"]
+    (tmp_path / "frame_01.jpg").write_bytes(b"")
+    assert pc.collect_filenames(str(tmp_path), "testing")[0] == [str(tmp_path / "frame_01.jpg")]
+    # camera selection (:253-268), including the reference's substring behaviour
+    assert pc.cam_file_for("x/SyntheticColon_I/Frames_S1/f.png", "simcol", None) == "datasets/SyntheticColon/SyntheticColon_I/cam.txt"
+    assert pc.cam_file_for("x/SyntheticColon_III/Frames_O2/f.png", "simcol", None) == "datasets/SyntheticColon/SyntheticColon_I/cam.txt"
+    assert pc.cam_file_for("f.png", None, "my_cam.txt") == "my_cam.txt"
+    with pytest.raises(ValueError):
+        pc.cam_file_for("x/other/f.png", "simcol", None)
+    with pytest.raises(ValueError):
+        pc.cam_file_for("f.png", None, None)
+    # pose (:53-69) against scipy, un-normalised quaternion in the file
+    (tmp_path / "p.txt").write_text("0.1 -0.2 0.3")
+    (tmp_path / "q.txt").write_text("0.2 0.4 -0.2 1.6")
+    T = pc.load_transformation(str(tmp_path / "p.txt"), str(tmp_path / "q.txt"))
+    np.testing.assert_allclose(T[:3, :3], Rotation.from_quat([0.2, 0.4, -0.2, 1.6]).as_matrix(), atol=1e-15)
+    np.testing.assert_allclose(T[:, 3], [0.1, -0.2, 0.3, 1.0])
+    # checkpoint (:163-185)
+    lin = torch.nn.Linear(2, 2)
+    w = torch.full((2, 2), 0.5)
+    torch.save({"state_dict": {"model.weight": w, "model.bias": torch.zeros(2)}}, tmp_path / "a.ckpt")
+    pc.load_checkpoint(lin, str(tmp_path / "a.ckpt"))
+    assert torch.equal(lin.weight.data, w)
+    torch.save({"weight": 2 * w, "bias": torch.zeros(2)}, tmp_path / "b.pth")
+    pc.load_checkpoint(lin, str(tmp_path / "b.pth"))
+    assert torch.equal(lin.weight.data, 2 * w)
