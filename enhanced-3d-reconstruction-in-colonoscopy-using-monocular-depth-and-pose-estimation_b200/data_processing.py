@@ -57,3 +57,37 @@ def load_item(input_path: str, target_path: str, transforms: SimColTransforms) -
     if depth.dtype != np.uint16:
         depth = depth.astype(np.float32)
     return transforms(image, depth)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose-pair items (reference ``data_processing/pose_estimation.py:205-311``): the same frame / depth transforms, two
+# consecutive frames stacked to 8 channels, and the relative-pose target computed from the absolute poses.
+# ------------------------------------------------------------------------------------------------
+def relative_pose_targets(poses) -> torch.Tensor:
+    """Absolute poses [N,7] (xyz + quaternion xyzw) -> the N-1 targets of ``PoseDataset.__getitem__`` (:245-303), all pairs
+    at once with the item code's own fp32 operations in its order: unit translation direction
+    ``(p2 - p1) / (|p2 - p1| + 1e-8)`` and ``normalize(q2 (x) conj(q1), eps=1e-8)`` with the product written as the
+    reference writes it."""
+    P = torch.as_tensor(np.asarray(poses) if not torch.is_tensor(poses) else poses).to(torch.float32)
+    if P.dim() != 2 or P.shape[1] != 7:
+        raise ValueError(f"poses must be [N,7], got {tuple(P.shape)}")
+    p1, p2, qa, q2 = P[:-1, :3], P[1:, :3], P[:-1, 3:], P[1:, 3:]
+    rel = p2 - p1
+    rel = rel / (torch.linalg.vector_norm(rel, dim=1, keepdim=True) + 1e-8)
+    q1 = qa * torch.tensor([-1.0, -1.0, -1.0, 1.0], dtype=torch.float32, device=P.device)  # conjugate (:262-264)
+    x = q2[:, 0] * q1[:, 3] + q2[:, 1] * q1[:, 2] - q2[:, 2] * q1[:, 1] + q2[:, 3] * q1[:, 0]
+    y = -q2[:, 0] * q1[:, 2] + q2[:, 1] * q1[:, 3] + q2[:, 2] * q1[:, 0] + q2[:, 3] * q1[:, 1]
+    z = q2[:, 0] * q1[:, 1] - q2[:, 1] * q1[:, 0] + q2[:, 2] * q1[:, 3] + q2[:, 3] * q1[:, 2]
+    w = -q2[:, 0] * q1[:, 0] - q2[:, 1] * q1[:, 1] - q2[:, 2] * q1[:, 2] + q2[:, 3] * q1[:, 3]
+    q = torch.nn.functional.normalize(torch.stack([x, y, z, w], dim=1), dim=1, eps=1e-8)
+    return torch.cat([rel, q], dim=1)
+
+
+def pose_pair_items(images, depths, poses, transforms: SimColTransforms) -> dict:
+    """A sequence of N decoded frames (uint8 [N,H,W,3]) and depths (uint16 [N,H,W]) with absolute poses [N,7] ->
+    ``{"input": [N-1,8,S,S], "target": [N-1,7]}``: every frame goes through the transforms ONCE (the reference's loader
+    transforms each frame twice, as the second half of pair i-1 and the first half of pair i), then
+    ``cat(rgb_i, depth_i, rgb_{i+1}, depth_{i+1})`` (:229-243)."""
+    from .pose_estimation_model import stack_pairs
+    rgb, d = transforms.transform_input(images), transforms.transform_output(depths)
+    return {"input": stack_pairs(rgb, d), "target": relative_pose_targets(poses).to(rgb.device)}

@@ -41,3 +41,24 @@ def build_pose_oracle(in_channels: int = 8, seed: int = 0) -> nn.Module:
 
     net.forward = forward
     return net
+
+
+def relative_pose_item(pose1, pose2) -> torch.Tensor:
+    """ONE item's target exactly as ``PoseDataset.__getitem__`` computes it (data_processing/pose_estimation.py:245-303):
+    per-item scalar torch fp32 code, restated line by line (the dataset class itself needs the SimCol files)."""
+    import torch.nn.functional as F
+
+    pos1 = torch.tensor(pose1[:3], dtype=torch.float32)
+    pos2 = torch.tensor(pose2[:3], dtype=torch.float32)
+    quat1 = torch.tensor(pose1[3:], dtype=torch.float32)
+    quat2 = torch.tensor(pose2[3:], dtype=torch.float32)
+    relative_pos = pos2 - pos1
+    relative_pos = relative_pos / (torch.norm(relative_pos) + 1e-8)
+    q1_inv = quat1 * torch.tensor([-1, -1, -1, 1], dtype=torch.float32)
+    rq = torch.zeros(4, dtype=torch.float32)
+    rq[0] = quat2[0] * q1_inv[3] + quat2[1] * q1_inv[2] - quat2[2] * q1_inv[1] + quat2[3] * q1_inv[0]
+    rq[1] = -quat2[0] * q1_inv[2] + quat2[1] * q1_inv[3] + quat2[2] * q1_inv[0] + quat2[3] * q1_inv[1]
+    rq[2] = quat2[0] * q1_inv[1] - quat2[1] * q1_inv[0] + quat2[2] * q1_inv[3] + quat2[3] * q1_inv[2]
+    rq[3] = -quat2[0] * q1_inv[0] - quat2[1] * q1_inv[1] - quat2[2] * q1_inv[2] + quat2[3] * q1_inv[3]
+    rq = F.normalize(rq, dim=0, eps=1e-8)
+    return torch.cat([relative_pos, rq])

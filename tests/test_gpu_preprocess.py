@@ -69,3 +69,23 @@ def test_load_item_files(tmp_path):
     item = load_item(str(tmp_path / "FrameBuffer_0000.png"), str(tmp_path / "Depth_0000.png"), SimColTransforms(70))
     assert item["image"].shape == (3, 70, 70) and item["depth"].shape == (1, 70, 70)
     assert -0.3 <= float(item["depth"].min()) and float(item["depth"].max()) <= 1.3  # [0, 1] plus bicubic over/undershoot
+
+
+def test_pose_pair_items():
+    """data_processing.pose_pair_items (pose_estimation.py:205-311): every frame transformed once, pairs stacked to 8
+    channels in the order rgb_i, depth_i, rgb_{i+1}, depth_{i+1}, targets from the absolute poses."""
+    from dav2_b200.data_processing import SimColTransforms, pose_pair_items, relative_pose_targets
+    rng = np.random.default_rng(2)
+    N, H, W, S = 5, 95, 95, 70
+    imgs = rng.integers(0, 255, size=(N, H, W, 3), dtype=np.uint8)
+    deps = rng.integers(0, 65535, size=(N, H, W), dtype=np.uint16)
+    poses = np.concatenate([rng.normal(0, 1, (N, 3)), rng.normal(0, 1, (N, 4))], 1)
+    poses[:, 3:] /= np.linalg.norm(poses[:, 3:], axis=1, keepdims=True)
+    tr = SimColTransforms(S)
+    item = pose_pair_items(imgs, deps, poses, tr)
+    assert item["input"].shape == (N - 1, 8, S, S) and item["input"].is_cuda and item["target"].shape == (N - 1, 7)
+    for i in range(N - 1):
+        one_a, one_b = tr(imgs[i], deps[i]), tr(imgs[i + 1], deps[i + 1])
+        want = torch.cat([one_a["image"], one_a["depth"], one_b["image"], one_b["depth"]], 0)
+        assert torch.equal(item["input"][i], want)
+    assert torch.equal(item["target"].cpu(), relative_pose_targets(poses))

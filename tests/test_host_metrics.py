@@ -207,3 +207,25 @@ def test_pointcloud_dav2_host_side(tmp_path):
     torch.save({"weight": 2 * w, "bias": torch.zeros(2)}, tmp_path / "b.pth")
     pc.load_checkpoint(lin, str(tmp_path / "b.pth"))
     assert torch.equal(lin.weight.data, 2 * w)
+
+
+def test_relative_pose_targets_match_item_code():
+    """data_processing.relative_pose_targets (all pairs at once) == the reference loader's per-item code
+    (pose_estimation.py:245-303, restated in oracle/pose_oracle.py), including a repeated pose (zero motion)."""
+    from oracle import pose_oracle as PO
+    from dav2_b200 import data_processing as dp
+    rng = np.random.default_rng(3)
+    N = 40
+    pos = np.cumsum(rng.normal(0, 0.01, (N, 3)), axis=0)
+    q = rng.normal(0, 1, (N, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    poses = np.concatenate([pos, q], 1)
+    poses[7] = poses[6]  # identical consecutive poses: 0 / 1e-8 translation, identity rotation
+    got = dp.relative_pose_targets(poses)
+    assert got.shape == (N - 1, 7) and got.dtype == torch.float32
+    want = torch.stack([PO.relative_pose_item(poses[i], poses[i + 1]) for i in range(N - 1)])
+    assert torch.allclose(got, want, rtol=0, atol=2e-7), float((got - want).abs().max())
+    assert torch.equal(got[6, :3], torch.zeros(3)) and abs(float(got[6, 6])) > 0.999999
+    assert torch.allclose(got[:, 3:].norm(dim=1), torch.ones(N - 1), atol=1e-6)
+    with pytest.raises(ValueError):
+        dp.relative_pose_targets(np.zeros((4, 6)))
