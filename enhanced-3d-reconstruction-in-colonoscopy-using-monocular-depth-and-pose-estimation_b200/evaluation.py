@@ -163,17 +163,49 @@ def evaluate_trajectory(pred_rel_poses: torch.Tensor, gt_rel_poses: torch.Tensor
             "rote": compute_rot_error(gt_abs[:, 3:], pred_abs[:, 3:])}
 
 
+class RunningMeans:
+    """Stand-in for the reference's ``MetricCollection`` of ``MeanMetric`` (lightning_model.py:143-150,
+    pose_estimation_model.py:146-152): per key a running (sum, count) kept where the values live -- on the device for
+    device tensors, so nothing synchronises until ``compute``."""
+
+    def __init__(self, keys):
+        self.keys = tuple(keys)
+        self._acc: Optional[torch.Tensor] = None  # fp64 [len(keys)] sums
+        self._n = 0
+
+    def reset(self) -> None:
+        self._acc, self._n = None, 0
+
+    def update(self, metrics: dict) -> None:
+        vals = [torch.as_tensor(metrics[k]).detach().to(torch.float64).reshape(()) for k in self.keys]
+        dev = next((v.device for v in vals if v.is_cuda), vals[0].device)
+        v = torch.stack([x.to(dev) for x in vals])
+        self._acc = v.clone() if self._acc is None else self._acc + v.to(self._acc.device)
+        self._n += 1
+
+    def compute(self) -> dict:
+        if self._acc is None:
+            return {k: float("nan") for k in self.keys}
+        return dict(zip(self.keys, (self._acc / self._n).tolist()))
+
+
 # ------------------------------------------------------------------------------------------------
-# Per-procedure aggregation of test_lightning.py:27-111 / :240-274 (host bookkeeping; no Lightning needed)
+# Per-procedure aggregation of test_lightning.py:27-111 / :240-274 and pose_estimation_lightning.py:43-185 (host
+# bookkeeping; no Lightning needed)
 # ------------------------------------------------------------------------------------------------
+DEPTH_KEYS = ("l1", "abs_rel", "d1", "rmse")
+POSE_KEYS = ("ate", "rte", "rote")
+
+
 class ProcedureMetricCollector:
     """The reference appends the BATCH metric once per frame to the frame's procedure bucket
-    (test_lightning.py:76-109) and reports mean over procedures of per-procedure means (:244-274)."""
+    (test_lightning.py:76-109) and reports mean over procedures of per-procedure means (:244-274).
+    ``keys=POSE_KEYS`` gives the pose test's collector (pose_estimation_lightning.py:43-185: same bucketing over
+    ``batch["dataset"]`` / ``batch["id"]``, metrics ate / rte / rote)."""
 
-    KEYS = ("l1", "abs_rel", "d1", "rmse")
-
-    def __init__(self):
+    def __init__(self, keys=DEPTH_KEYS):
         from collections import defaultdict
+        self.KEYS = tuple(keys)
         self.metrics_by_procedure = defaultdict(list)
 
     @staticmethod

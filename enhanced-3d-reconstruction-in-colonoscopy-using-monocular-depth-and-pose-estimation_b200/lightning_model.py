@@ -25,28 +25,6 @@ from .dpt import MODEL_CONFIGS, DepthAnythingV2  # MODEL_CONFIGS: lightning_mode
 METRIC_KEYS = ("d1", "abs_rel", "rmse", "l1")
 
 
-class _DeviceMeans:
-    """Stand-in for the MetricCollection of MeanMetric (lightning_model.py:143-150): per key a running
-    (sum, count) pair kept on the device, no host synchronisation until ``compute``."""
-
-    def __init__(self):
-        self._acc: Optional[torch.Tensor] = None  # fp64 [len(METRIC_KEYS)] sums
-        self._n = 0
-
-    def reset(self) -> None:
-        self._acc, self._n = None, 0
-
-    def update(self, metrics: dict) -> None:
-        v = torch.stack([torch.as_tensor(metrics[k]).to(torch.float64) for k in METRIC_KEYS])
-        self._acc = v.clone() if self._acc is None else self._acc + v.to(self._acc.device)
-        self._n += 1
-
-    def compute(self) -> dict:
-        if self._acc is None:
-            return {k: float("nan") for k in METRIC_KEYS}
-        return dict(zip(METRIC_KEYS, (self._acc / self._n).tolist()))
-
-
 class DepthAnythingV2Module:
     """``DepthAnythingV2Module(encoder, min_depth, max_depth, ...)`` with the reference's test / predict
     surface.  ``pretrained_from``: a ``depth_anything_v2_metric_hypersim_{encoder}.pth``-style file whose
@@ -68,7 +46,7 @@ class DepthAnythingV2Module:
             self.model.load_state_dict({k: v for k, v in sd.items() if "pretrained" in k}, strict=False)
         elif pretrained_from is not None:
             raise FileNotFoundError(pretrained_from)
-        self.metric = _DeviceMeans()
+        self.metric = evaluation.RunningMeans(METRIC_KEYS)
         self.logged: dict = {}
 
     # ---- nn.Module-like plumbing the test driver uses -------------------------------------------------

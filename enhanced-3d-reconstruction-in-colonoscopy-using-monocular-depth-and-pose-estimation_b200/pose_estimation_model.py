@@ -121,3 +121,97 @@ def stack_pairs(rgb: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
     (data_processing/pose_estimation.py:229-243)."""
     f = torch.cat([rgb, depth], dim=1)
     return torch.cat([f[:-1], f[1:]], dim=1).contiguous()
+
+
+class PoseEstimationModule:
+    """Inference-side drop-in for the reference's ``PoseEstimationModule`` (pose_estimation_model.py:108-170 constructor /
+    forward, :295-343 test hooks): ``test_step`` predicts the relative poses of a batch of stacked pairs, keeps them for the
+    trajectory evaluation and returns the per-batch ``compute_pose_errors``; ``on_test_epoch_end`` scale-aligns and composes
+    the whole trajectory (``evaluation.evaluate_trajectory``, pose chain on the GPU kernel).  No Lightning import; the
+    training hooks are outside the path and raise."""
+
+    KEYS = ("ate", "rte", "rote")
+
+    def __init__(self, in_channels: int = 8, precision: str = "fp16", **hparams):
+        from types import SimpleNamespace
+        from . import evaluation
+        self.hparams = SimpleNamespace(in_channels=in_channels, **hparams)
+        self.model = PoseEstimationNet(in_channels=in_channels, precision=precision)
+        self.metric = evaluation.RunningMeans(self.KEYS)
+        self.current_trajectory_preds: list = []
+        self.current_trajectory_gts: list = []
+        self.trajectory_metrics: list = []
+        self.logged: dict = {}
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.model.parameters()).device
+
+    def to(self, device):
+        self.model = self.model.to(device)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def eval(self):
+        self.model.eval()
+        return self
+
+    def state_dict(self) -> dict:
+        return {f"model.{k}": v for k, v in self.model.state_dict().items()}
+
+    def load_state_dict(self, state_dict: dict, strict: bool = True):
+        sd = {k[len("model."):]: v for k, v in state_dict.items() if k.startswith("model.")}
+        extra = [k for k in state_dict if not k.startswith("model.")]
+        if strict and extra:
+            raise RuntimeError(f"unexpected keys in state_dict: {extra[:4]}")
+        return self.model.load_state_dict(sd, strict=strict)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.model(x)
+
+    __call__ = forward
+
+    def log(self, name: str, value) -> None:
+        self.logged[name] = float(value)
+
+    def on_test_epoch_start(self) -> None:
+        self.metric.reset()
+        self.current_trajectory_preds, self.current_trajectory_gts, self.trajectory_metrics = [], [], []
+
+    @torch.no_grad()
+    def test_step(self, batch: dict, batch_idx: int = 0) -> dict:
+        from . import evaluation
+        pred = self(batch["input"])
+        target = batch["target"]
+        self.current_trajectory_preds.append(pred.detach().cpu())
+        self.current_trajectory_gts.append(target.detach().cpu())
+        metrics = evaluation.compute_pose_errors(pred.detach(), target.detach())
+        self.metric.update(metrics)
+        for k, v in metrics.items():
+            self.log(f"Test/test_{k}", v)
+        return metrics
+
+    def on_test_epoch_end(self) -> dict:
+        from . import evaluation
+        # the reference stacks the per-batch tensors ([batches, B, 7], equal batch sizes required) and hands the 3-D stack
+        # to evaluate_trajectory (:321-330); kept as is
+        pred = torch.stack(self.current_trajectory_preds)
+        gt = torch.stack(self.current_trajectory_gts)
+        traj = evaluation.evaluate_trajectory(pred_rel_poses=pred, gt_rel_poses=gt, initial_pose=None)
+        for k, v in traj.items():
+            self.log(f"Test/trajectory_{k}", v)
+        self.trajectory_metrics.append(traj)
+        self.current_trajectory_preds, self.current_trajectory_gts = [], []
+        final = self.metric.compute()
+        for k, v in final.items():
+            self.log(f"Test/test_{k}", v)
+        self.metric.reset()
+        return {"trajectory": traj, "mean": final}
+
+    def training_step(self, *a, **k):
+        raise NotImplementedError("dav2_b200 is the inference path; training stays with the reference")
+
+    validation_step = configure_optimizers = pose_loss = training_step

@@ -169,10 +169,40 @@ def config1_fixture():
     print("config1:", depth.min(), depth.max(), depth.mean(), depth.std())
 
 
+def pose_module_fixture():
+    """tests/golden/pose_module_small.npz: what PoseEstimationModule's test hooks compute (pose_estimation_model.py:302-343)
+    for 5 batches of 8 pairs -- per-batch compute_pose_errors and evaluate_trajectory on the STACKED [5,8,7] tensors, both
+    by executing the reference's eval/evaluation.py."""
+    import numpy as np
+    import torch
+    from scipy.spatial.transform import Rotation as R
+    sys.path.insert(0, REF)
+    from eval import evaluation as ref
+    rng = np.random.default_rng(91)
+    nb, B = 5, 8
+    t = rng.normal(0, 1.0, size=(nb, B, 3))
+    t /= np.linalg.norm(t, axis=2, keepdims=True)
+    q = R.from_rotvec(np.deg2rad(rng.normal(0, 2.0, size=(nb * B, 3)))).as_quat().reshape(nb, B, 4)
+    gt = np.concatenate([t, q], 2).astype(np.float32)
+    pred = gt + rng.normal(0, 0.03, size=gt.shape).astype(np.float32)
+    per_batch = []
+    for b in range(nb):
+        m = ref.compute_pose_errors(torch.from_numpy(pred[b]), torch.from_numpy(gt[b]))
+        per_batch.append([float(m["ate"]), float(m["rte"]), float(m["rote"])])
+    traj = ref.evaluate_trajectory(pred_rel_poses=torch.from_numpy(pred.copy()), gt_rel_poses=torch.from_numpy(gt.copy()),
+                                   initial_pose=None)
+    np.savez_compressed(os.path.join(OUT, "pose_module_small.npz"), gt=gt, pred=pred, per_batch=np.array(per_batch),
+                        traj=np.array([float(traj["ate"]), float(traj["rte"]), float(traj["rote"])]))
+    print("pose module:", per_batch[0], traj)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config1":
         config1_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pose_module":
+        pose_module_fixture()
     else:
         main()
         pose_metric_fixtures()
+        pose_module_fixture()
         config1_fixture()

@@ -151,7 +151,8 @@ def test_lightning_module_surface():
         lm.DepthAnythingV2Module(encoder="vitg")
     with pytest.raises(FileNotFoundError):
         lm.DepthAnythingV2Module(encoder="vits", pretrained_from="/nonexistent/ckpt.pth")
-    means = lm._DeviceMeans()
+    from dav2_b200.evaluation import RunningMeans
+    means = RunningMeans(lm.METRIC_KEYS)
     assert all(np.isnan(v) for v in means.compute().values())
     means.update({"d1": 0.5, "abs_rel": 1.0, "rmse": 2.0, "l1": 3.0})
     means.update({"d1": torch.tensor(1.0), "abs_rel": torch.tensor(3.0), "rmse": torch.tensor(4.0), "l1": torch.tensor(5.0)})
@@ -229,3 +230,55 @@ def test_relative_pose_targets_match_item_code():
     assert torch.allclose(got[:, 3:].norm(dim=1), torch.ones(N - 1), atol=1e-6)
     with pytest.raises(ValueError):
         dp.relative_pose_targets(np.zeros((4, 6)))
+
+
+def _pose_module_with_fixture_preds(g):
+    """PoseEstimationModule whose network is replaced by the fixture's predictions: the hooks' bookkeeping is under test."""
+    from dav2_b200.pose_estimation_model import PoseEstimationModule
+    mod = PoseEstimationModule(in_channels=8, lr=1e-4)
+    preds = iter(torch.from_numpy(g["pred"]))
+    mod.model = lambda x: next(preds).to(x.device)
+    return mod
+
+
+def test_pose_module_test_step_matches_reference(golden_dir):
+    """PoseEstimationModule.test_step (pose_estimation_model.py:302-317): per-batch ate / rte / rote equal the executed
+    reference's; state-dict prefix handling; pose collector keys."""
+    from dav2_b200.evaluation import POSE_KEYS, ProcedureMetricCollector
+    from dav2_b200.pose_estimation_model import PoseEstimationModule
+    g = np.load(os.path.join(golden_dir, "pose_module_small.npz"))
+    real = PoseEstimationModule(in_channels=8, lr=1e-4)
+    assert real.hparams.lr == 1e-4 and all(k.startswith("model.") for k in real.state_dict())
+    real.load_state_dict(real.state_dict())
+    with pytest.raises(RuntimeError):
+        real.load_state_dict({**real.state_dict(), "criterion.w": torch.zeros(1)})
+    with pytest.raises(NotImplementedError):
+        real.training_step({})
+    mod = _pose_module_with_fixture_preds(g)
+    coll = ProcedureMetricCollector(POSE_KEYS)
+    mod.on_test_epoch_start()
+    for b in range(g["gt"].shape[0]):
+        batch = {"input": torch.zeros(8, 8, 4, 4), "target": torch.from_numpy(g["gt"][b]),
+                 "dataset": ["d/SyntheticColon_II"] * 8, "id": [f"B{b + 1}_{j:04d}" for j in range(8)]}
+        out = mod.test_step(batch, b)
+        np.testing.assert_allclose([float(out[k]) for k in POSE_KEYS], g["per_batch"][b], rtol=1e-4, atol=1e-6)
+        coll.on_test_batch_end(out, batch)
+    assert len(mod.current_trajectory_preds) == 5 and mod.current_trajectory_preds[0].shape == (8, 7)
+    s = coll.summary()
+    assert abs(s["per_procedure"]["SyntheticColon_II/Frames_B2"]["rote"] - g["per_batch"][1][2]) < 1e-4
+    np.testing.assert_allclose(mod.metric.compute()["ate"], g["per_batch"][:, 0].mean(), rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_pose_module_epoch_end_matches_reference(golden_dir):
+    """on_test_epoch_end (:319-343): evaluate_trajectory on the stacked per-batch tensors, as the reference executes it."""
+    g = np.load(os.path.join(golden_dir, "pose_module_small.npz"))
+    mod = _pose_module_with_fixture_preds(g)
+    mod.on_test_epoch_start()
+    for b in range(g["gt"].shape[0]):
+        mod.test_step({"input": torch.zeros(8, 8, 4, 4), "target": torch.from_numpy(g["gt"][b])}, b)
+    out = mod.on_test_epoch_end()
+    np.testing.assert_allclose([float(out["trajectory"][k]) for k in ("ate", "rte", "rote")], g["traj"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose([out["mean"][k] for k in ("ate", "rte", "rote")], g["per_batch"].mean(0), rtol=1e-4)
+    assert set(mod.logged) == {f"Test/{p}_{k}" for p in ("test", "trajectory") for k in ("ate", "rte", "rote")}
+    assert mod.current_trajectory_preds == []
