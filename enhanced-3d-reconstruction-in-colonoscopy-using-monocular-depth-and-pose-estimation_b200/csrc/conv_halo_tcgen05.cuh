@@ -8,7 +8,10 @@
 // descriptor whose start address is shifted by dy*2048 + dx*128 bytes and whose 8-row groups are
 // 2048 B apart (a 16-pixel line pitch keeps every group 1024 B-aligned relative to the start, so the
 // 128B-swizzle phase is the same for all groups).  A traffic drops 9 x 16 KB -> 36 KB per channel block.
-// Weights (B) stream through their own ring, one [BN/2 x 64] tile per tap.
+// Weights (B) stream through their own ring, one [BN/2 x 64] tile per tap -- except for the N = 32 depth head, whose
+// whole weight set (<= 18 tiles of 2 KB per CTA) is loaded ONCE per CTA and stays resident: with the ring that kernel
+// moved 15.2 GB through the L2->SM crossbar per launch (10.1 GB of halo patches + 5.0 GB of re-streamed weights) at the
+// fabric's ~7.9 TB/s, i.e. it was crossbar-bound (profiles/ncu_conv_r02.txt).
 //
 // Tile = 16 rows x 8 columns of output pixels (M = 128 per CTA, 256 per CTA pair); roles, TMEM double
 // buffering, 8 epilogue warps and the fused epilogue are those of gemm2_tcgen05_kernel.
@@ -25,10 +28,11 @@ struct ConvHaloCfg {
   static constexpr int A_BYTES = HALO_H * HALO_W * 128; // 36864: [18][16] pixels x 64 channels x 2 B
   static constexpr int A_STAGES = 2;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;     // this CTA's half of one tap's weight tile
-  static constexpr int B_STAGES = BN == 256 ? 5 : 8;
+  static constexpr bool RESIDENT_B = BN == 32;          // depth head: all (tap, channel-block) weight tiles stay in smem
+  static constexpr int B_STAGES = BN == 256 ? 5 : (RESIDENT_B ? 18 : 8);   // resident: 9 taps x <= 2 channel blocks
   static constexpr int EPI_WARPS = BN >= 128 ? 8 : 4;    // N = 32 (depth head): one warp per TMEM lane quadrant holds the whole row
   static constexpr int HN = BN / (EPI_WARPS / 4);        // accumulator columns drained per epilogue warp
-  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * ::dav2::STG_ROW_BYTES;
+  static constexpr int STAGING_BYTES = RESIDENT_B ? 0 : EPI_WARPS * 32 * ::dav2::STG_ROW_BYTES;  // the head epilogue stores straight from registers
   static constexpr int VEC_BYTES = EPI_WARPS * HN * 4;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
@@ -59,7 +63,8 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t staging = sB + BS * Cfg::B_BYTES;
   const uint32_t vecs = staging + Cfg::STAGING_BYTES;
   const uint32_t bars = vecs + Cfg::VEC_BYTES;
-  constexpr int NBAR = 2 * AS + 2 * BS + 4;
+  constexpr int BB = Cfg::RESIDENT_B ? 1 : BS;  // weight barriers: one "all resident tiles landed", or a full/empty pair per ring stage
+  constexpr int NBAR = 2 * AS + 2 * BB + 4;
   static_assert(NBAR * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
   const uint32_t tmem_slot = bars + 8 * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
@@ -67,9 +72,9 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #define AFULL(s) (bars + 8u * (uint32_t)(s))
 #define AEMPTY(s) (bars + 8u * (uint32_t)(AS + (s)))
 #define BFULL(s) (bars + 8u * (uint32_t)(2 * AS + (s)))
-#define BEMPTY(s) (bars + 8u * (uint32_t)(2 * AS + BS + (s)))
-#define TFULL_BAR(a) (bars + 8u * (uint32_t)(2 * AS + 2 * BS + (a)))
-#define TEMPTY_BAR(a) (bars + 8u * (uint32_t)(2 * AS + 2 * BS + 2 + (a)))
+#define BEMPTY(s) (bars + 8u * (uint32_t)(2 * AS + BB + (s)))
+#define TFULL_BAR(a) (bars + 8u * (uint32_t)(2 * AS + 2 * BB + (a)))
+#define TEMPTY_BAR(a) (bars + 8u * (uint32_t)(2 * AS + 2 * BB + 2 + (a)))
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +85,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < AS; ++s) { mbar_init(AFULL(s), 1); mbar_init(AEMPTY(s), 1); }
-    for (int s = 0; s < BS; ++s) { mbar_init(BFULL(s), 1); mbar_init(BEMPTY(s), 1); }
+    for (int s = 0; s < BB; ++s) { mbar_init(BFULL(s), 1); mbar_init(BEMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 2 * Cfg::EPI_WARPS); }
     fence_mbar_init();
   }
@@ -99,6 +104,15 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ================================ TMA producer (both CTAs; whole warp, elected lane issues) ======
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
+    if constexpr (Cfg::RESIDENT_B) {
+      // tiles_n == 1: every (tap, channel block) tile of this CTA's half of the output channels, once
+      if (pt0 < num_pt && elect_one()) {
+        if (leader) mbar_expect_tx(BFULL(0), 2u * Cfg::B_BYTES * (uint32_t)p.num_kb);
+        for (int t = 0; t < p.num_kb; ++t)
+          tma_load_2d_2sm(sB + t * Cfg::B_BYTES, &tmB, mapa_shared(BFULL(0), 0), t * 64, (int)rank * (BN / 2));
+      }
+      __syncwarp();
+    }
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
       const int tmp = pt / p.tiles_n, tn = pt - tmp * p.tiles_n;
       const int tm = 2 * tmp + (int)rank;
@@ -114,7 +128,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
         if (++sa == AS) { sa = 0; pha ^= 1u; }
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < (Cfg::RESIDENT_B ? 0 : 9); ++tap) {
           mbar_wait(BEMPTY(sb), phb ^ 1u);
           if (elect_one()) {
             if (leader) mbar_expect_tx(BFULL(sb), 2 * Cfg::B_BYTES);
@@ -133,6 +147,10 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t pha = 0, phb = 0;
     int as = 0;
     uint32_t aphase = 0;
+    if constexpr (Cfg::RESIDENT_B) {
+      if (pt0 < num_pt) mbar_wait(BFULL(0), 0);
+      tc_fence_after();
+    }
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
       mbar_wait(TEMPTY_BAR(as), aphase ^ 1u);
       tc_fence_after();
@@ -144,8 +162,12 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
-          mbar_wait(BFULL(sb), phb);
-          tc_fence_after();
+          if constexpr (Cfg::RESIDENT_B) {
+            sb = tap * p.cblocks + cb;  // the weight matrix's K order: (tap, channel block)
+          } else {
+            mbar_wait(BFULL(sb), phb);
+            tc_fence_after();
+          }
           // rows of one 8-pixel group are contiguous (8 x 128 B); groups (output rows) are one 16-pixel line apart
           const uint64_t adesc = make_sw128_desc_bo(a_base + (uint32_t)(dy * Cfg::HALO_W + dx) * 128u, 16, Cfg::HALO_W * 128,
                                                     bo_mode ? (uint32_t)dx : 0u);
@@ -154,12 +176,14 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_h16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((cb | tap | k) != 0));
-            umma_commit_2sm_mc(BEMPTY(sb), 3);
+            if constexpr (!Cfg::RESIDENT_B) umma_commit_2sm_mc(BEMPTY(sb), 3);
             if (tap == 8) umma_commit_2sm_mc(AEMPTY(sa), 3);
             if (tap == 8 && cb == p.cblocks - 1) umma_commit_2sm_mc(TFULL_BAR(as), 3);
           }
           __syncwarp();
-          if (++sb == BS) { sb = 0; phb ^= 1u; }
+          if constexpr (!Cfg::RESIDENT_B) {
+            if (++sb == BS) { sb = 0; phb ^= 1u; }
+          }
         }
         if (++sa == AS) { sa = 0; pha ^= 1u; }
       }

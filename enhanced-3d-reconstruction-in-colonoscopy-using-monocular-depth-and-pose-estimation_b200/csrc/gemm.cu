@@ -124,6 +124,10 @@ static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   }
   const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
   if (pairs <= 0) return 0;
+  if (Cfg::RESIDENT_B && (p.num_kb > Cfg::B_STAGES || p.tiles_n != 1)) {
+    set_last_error("conv_halo<%d>: %d weight tiles do not fit the resident set (%d)", BN, p.num_kb, Cfg::B_STAGES);
+    return -3;
+  }
   // the N=32 head variant needs ~110 KB smem and 64 TMEM columns: two CTA pairs fit per TPC
   const int max_pairs = (sm_count() / 2) * (Cfg::SMEM_BYTES <= 112 * 1024 ? 2 : 1);
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
