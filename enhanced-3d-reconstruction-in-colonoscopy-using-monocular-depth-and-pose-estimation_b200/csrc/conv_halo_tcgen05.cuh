@@ -3,15 +3,18 @@
 // The plain implicit-GEMM path loads one shifted 128-pixel A box per (tap, channel block): every input
 // element crosses L2->smem 9 times, and with N <= 256 every A box is private to one CTA, so the DPT
 // convs were bound by the ~7-8 TB/s L2->SM fabric (ncu: 64-96 B/clk/SM demanded), not by the tensor pipe.
-// Here each CTA loads, per 64-channel block, ONE halo patch of (16+2) x (8+2 -> padded to 16) pixels and
-// issues the MMAs of all 9 taps from it: tap (dy,dx) is the same smem patch read through a UMMA
-// descriptor whose start address is shifted by dy*2048 + dx*128 bytes and whose 8-row groups are
-// 2048 B apart (a 16-pixel line pitch keeps every group 1024 B-aligned relative to the start, so the
-// 128B-swizzle phase is the same for all groups).  A traffic drops 9 x 16 KB -> 36 KB per channel block.
+// Here each CTA loads, per 64-channel block, ONE halo patch of (16+2) x (8+2) pixels and issues the MMAs of
+// all 9 taps from it: tap (dy,dx) is the same smem patch read through a UMMA descriptor whose start
+// address is shifted by (dy*10 + dx)*128 bytes and whose 8-row groups are one 10-pixel line (1280 B)
+// apart.  Neither the start nor the group stride is a multiple of the 1024 B swizzle atom: that is fine
+// because both TMA (writing) and the MMA (reading) derive the 128B-swizzle phase from the absolute
+// shared-memory address bits, with every stage base 1024 B-aligned (the first version padded lines to
+// 16 pixels to keep all groups phase-aligned and moved 60 % more patch bytes for it; parity tests are
+// identical for both).  A traffic drops 9 x 16 KB -> 22.5 KB per channel block.
 // Weights (B) stream through their own ring, one [BN/2 x 64] tile per tap -- except for the N = 32 depth head, whose
 // whole weight set (<= 18 tiles of 2 KB per CTA) is loaded ONCE per CTA and stays resident: with the ring that kernel
-// moved 15.2 GB through the L2->SM crossbar per launch (10.1 GB of halo patches + 5.0 GB of re-streamed weights) at the
-// fabric's ~7.9 TB/s, i.e. it was crossbar-bound (profiles/ncu_conv_r02.txt).
+// moved 15.2 GB through the L2->SM crossbar per launch (10.1 GB of 16-wide halo patches + 5.0 GB of re-streamed weights)
+// at the fabric's ~7.9 TB/s, i.e. it was crossbar-bound (profiles/ncu_conv_r02.txt).
 //
 // Tile = 16 rows x 8 columns of output pixels (M = 128 per CTA, 256 per CTA pair); roles, TMEM double
 // buffering, 8 epilogue warps and the fused epilogue are those of gemm2_tcgen05_kernel.
@@ -19,14 +22,23 @@
 
 #include "gemm2_tcgen05.cuh"
 
+#ifndef HALO_A_STAGES
+#define HALO_A_STAGES 2  // halo patches in flight per CTA (A/B-measured: see DESIGN.md section 5)
+#endif
+
 namespace dav2 {
 
 template <int BN>
 struct ConvHaloCfg {
   static constexpr int TW = 8, TH = 16;                 // output tile (pixels)
-  static constexpr int HALO_W = 16, HALO_H = TH + 2;    // loaded patch: x0-1 .. x0+14, y0-1 .. y0+16
-  static constexpr int A_BYTES = HALO_H * HALO_W * 128; // 36864: [18][16] pixels x 64 channels x 2 B
-  static constexpr int A_STAGES = 2;
+#ifdef HALO_PATCH_W
+  static constexpr int HALO_W = HALO_PATCH_W, HALO_H = TH + 2;  // A/B builds only (16 = the round-1 line pitch)
+#else
+  static constexpr int HALO_W = TW + 2, HALO_H = TH + 2; // loaded patch: x0-1 .. x0+8, y0-1 .. y0+16
+#endif
+  static constexpr int A_TX_BYTES = HALO_H * HALO_W * 128; // 23040: [18][10] pixels x 64 channels x 2 B (what TMA delivers)
+  static constexpr int A_BYTES = (A_TX_BYTES + 1023) / 1024 * 1024;  // stage stride: keeps every stage 1024 B-aligned
+  static constexpr int A_STAGES = HALO_A_STAGES;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;     // this CTA's half of one tap's weight tile
   static constexpr bool RESIDENT_B = BN == 32;          // depth head: all (tap, channel-block) weight tiles stay in smem
   static constexpr int B_STAGES = BN == 256 ? 5 : (RESIDENT_B ? 18 : 8);   // resident: 9 taps x <= 2 channel blocks
@@ -123,7 +135,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int cb = 0; cb < p.cblocks; ++cb) {
         mbar_wait(AEMPTY(sa), pha ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(AFULL(sa), 2 * Cfg::A_BYTES);
+          if (leader) mbar_expect_tx(AFULL(sa), 2 * Cfg::A_TX_BYTES);
           tma_load_4d_2sm(sA + sa * Cfg::A_BYTES, &tmA, mapa_shared(AFULL(sa), 0), cb * 64, x0 - 1, y0 - 1, b);
         }
         __syncwarp();

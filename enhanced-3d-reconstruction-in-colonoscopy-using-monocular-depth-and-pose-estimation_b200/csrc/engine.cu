@@ -360,7 +360,7 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   const int tiles_m_all = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
   const bool two_cta = halo || gemm2_eligible(bn, mode, tiles_m_all);
   CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, (uint32_t)(halo ? 16 : tw),
+  if (int rc = make_tmap_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, (uint32_t)(halo ? ConvHaloCfg<256>::HALO_W : tw),
                               (uint32_t)(halo ? 18 : th))) return rc;
   if (int rc = make_tmap_2d(&tmB, Wp, (uint64_t)Cout, (uint64_t)Kp, (uint64_t)Kp, (uint32_t)(two_cta ? bn / 2 : bn))) return rc;
   p.M = B * H * W; p.N = Cout; p.K = Kp;
