@@ -58,7 +58,8 @@ print("\n".join(lines))
 shutil.copy(os.path.join(SRC, f"ncu_ops_metrics_{R}.csv"), os.path.join(DST, f"ncu_ops_metrics_{R}.csv"))
 
 # 3. details pages of the full captures
-for rep, out in ((f"prof_attn_{R}", f"ncu_attn_{R}.txt"), (f"prof_attn5477_{R}", f"ncu_attn5477_{R}.txt"), (f"prof_geom_{R}", f"ncu_geom_{R}.txt")):
+for rep, out in ((f"prof_attn_{R}", f"ncu_attn_{R}.txt"), (f"prof_attn5477_{R}", f"ncu_attn5477_{R}.txt"), (f"prof_geom_{R}", f"ncu_geom_{R}.txt"),
+                 (f"prof_conv_before_{R}", f"ncu_conv_before_{R}.txt"), (f"prof_conv_{R}", f"ncu_conv_{R}.txt")):
     p = os.path.join(SRC, rep + ".ncu-rep")
     if os.path.exists(p):
         txt = subprocess.run(["ncu", "-i", p, "--page", "details"], capture_output=True, text=True).stdout
