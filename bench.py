@@ -65,7 +65,7 @@ def csrc_sha16():
     return h.hexdigest()[:16]
 
 
-def measured_traffic():
+def measured_traffic(key="gemm_tcgen05_kernel_bytes_per_launch"):
     """DRAM bytes per launch of the dominant kernel from the committed ncu launch list -- only if that list was taken
     with THESE kernel sources (otherwise null: a constant from an older build would be stale)."""
     best = None
@@ -77,7 +77,7 @@ def measured_traffic():
             except ValueError:
                 continue
             if d.get("csrc_sha16") == csrc_sha16():
-                best = (d.get("gemm_tcgen05_kernel_bytes_per_launch"), f)
+                best = (d.get(key), f)
     return best if best else (None, None)
 
 
@@ -629,7 +629,10 @@ def main():
         bp = prof.get(key)
         if bp and bp["ms"] > 0:
             out[name] = {"bound": "hbm", "achieved": bp["bytes"] / (bp["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": bp["bytes"] / (bp["ms"] * 1e-3) / 1e9 / hbm, "traffic": None}
+                         "frac": bp["bytes"] / (bp["ms"] * 1e-3) / 1e9 / hbm,
+                         # DRAM bytes per launch from the committed launch list (same kernel sources only); the depth map
+                         # the pass reads was just written by the head conv, so part of it is served by L2
+                         "traffic": measured_traffic("backproject_kernel_bytes_per_launch")[0] if key == "backproject" and world == 1 and args.config == 3 else None}
     if bp_alone:
         gbs = B * HW * 21.0 / (bp_alone * 1e-3) / 1e9
         out["roofline_backproject_alone"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
