@@ -16,14 +16,18 @@
 // moved 15.2 GB through the L2->SM crossbar per launch (10.1 GB of 16-wide halo patches + 5.0 GB of re-streamed weights)
 // at the fabric's ~7.9 TB/s, i.e. it was crossbar-bound (profiles/ncu_conv_r02.txt).
 //
-// Tile = 16 rows x 8 columns of output pixels (M = 128 per CTA, 256 per CTA pair); roles, TMEM double
-// buffering, 8 epilogue warps and the fused epilogue are those of gemm2_tcgen05_kernel.
+// Tile = 16 rows x 8 columns of output pixels (M = 128 per CTA, 256 per CTA pair; N = 128 runs two such
+// tiles per CTA against every weight tile); roles, TMEM double buffering, 8 epilogue warps and the
+// fused epilogue are those of gemm2_tcgen05_kernel.
 #pragma once
 
 #include "gemm2_tcgen05.cuh"
 
 #ifndef HALO_A_STAGES
 #define HALO_A_STAGES 2  // halo patches in flight per CTA (A/B-measured: see DESIGN.md section 5)
+#endif
+#ifndef HALO_MT128
+#define HALO_MT128 2     // N = 128: pixel tiles per CTA that share every weight tile (1 = the one-tile form, for A/B builds)
 #endif
 
 namespace dav2 {
@@ -39,6 +43,11 @@ struct ConvHaloCfg {
   static constexpr int A_TX_BYTES = HALO_H * HALO_W * 128; // 23040: [18][10] pixels x 64 channels x 2 B (what TMA delivers)
   static constexpr int A_BYTES = (A_TX_BYTES + 1023) / 1024 * 1024;  // stage stride: keeps every stage 1024 B-aligned
   static constexpr int A_STAGES = HALO_A_STAGES;
+  // N = 128: 12.9 of the 17.4 GB a launch pulled through the L2->SM crossbar were weight tiles re-streamed for every
+  // 128-pixel tile.  With 256 accumulator columns free in TMEM a CTA keeps TWO pixel tiles in flight and issues both
+  // tiles' MMAs from each weight tile, halving that stream (N = 256 has no TMEM left for it and does not need it).
+  static constexpr int MT = BN == 128 ? HALO_MT128 : 1;
+  static constexpr int A_STAGE_BYTES = MT * A_BYTES;    // one stage = the halo patches of this CTA's MT tiles
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;     // this CTA's half of one tap's weight tile
   static constexpr bool RESIDENT_B = BN == 32;          // depth head: all (tap, channel-block) weight tiles stay in smem
   static constexpr int B_STAGES = BN == 256 ? 5 : (RESIDENT_B ? 18 : 8);   // resident: 9 taps x <= 2 channel blocks
@@ -46,10 +55,11 @@ struct ConvHaloCfg {
   static constexpr int HN = BN / (EPI_WARPS / 4);        // accumulator columns drained per epilogue warp
   static constexpr int STAGING_BYTES = RESIDENT_B ? 0 : EPI_WARPS * 32 * ::dav2::STG_ROW_BYTES;  // the head epilogue stores straight from registers
   static constexpr int VEC_BYTES = EPI_WARPS * HN * 4;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_BYTES + B_STAGES * B_BYTES + STAGING_BYTES + VEC_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE_BYTES + B_STAGES * B_BYTES + STAGING_BYTES + VEC_BYTES + BAR_BYTES;
+  static_assert(TMEM_COLS <= 512 && SMEM_BYTES <= 227 * 1024, "conv_halo resources");
 };
 
 // Same as make_sw128_desc plus the 3-bit "matrix base offset" field (bits 49-51).
@@ -63,7 +73,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvHaloCfg<BN>::THR
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p, const int bo_mode) {
   using Cfg = ConvHaloCfg<BN>;
-  constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
+  constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES, MT = Cfg::MT;
   static_assert(MODE == GM_CONV_BF16 || (MODE == GM_CONV_HEAD && BN == 32), "conv modes only");
   extern __shared__ uint8_t smem_raw[];
 
@@ -71,7 +81,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
   const uint32_t sA = base;
-  const uint32_t sB = sA + AS * Cfg::A_BYTES;
+  const uint32_t sB = sA + AS * Cfg::A_STAGE_BYTES;
   const uint32_t staging = sB + BS * Cfg::B_BYTES;
   const uint32_t vecs = staging + Cfg::STAGING_BYTES;
   const uint32_t bars = vecs + Cfg::VEC_BYTES;
@@ -80,7 +90,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   static_assert(NBAR * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
   const uint32_t tmem_slot = bars + 8 * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      base_ptr + AS * Cfg::A_BYTES + BS * Cfg::B_BYTES + Cfg::STAGING_BYTES + Cfg::VEC_BYTES + 8 * NBAR);
+      base_ptr + AS * Cfg::A_STAGE_BYTES + BS * Cfg::B_BYTES + Cfg::STAGING_BYTES + Cfg::VEC_BYTES + 8 * NBAR);
 #define AFULL(s) (bars + 8u * (uint32_t)(s))
 #define AEMPTY(s) (bars + 8u * (uint32_t)(AS + (s)))
 #define BFULL(s) (bars + 8u * (uint32_t)(2 * AS + (s)))
@@ -107,7 +117,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int pairs_m = (p.tiles_m + 1) >> 1;
+  const int pairs_m = (p.tiles_m + 2 * MT - 1) / (2 * MT);  // a CTA pair advances by 2 * MT pixel tiles
   const int num_pt = pairs_m * p.tiles_n;
   const int pt0 = (int)(blockIdx.x >> 1), pt_stride = (int)(gridDim.x >> 1);
   const int per_img = p.tiles_x * p.tiles_y;
@@ -127,16 +137,24 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
       const int tmp = pt / p.tiles_n, tn = pt - tmp * p.tiles_n;
-      const int tm = 2 * tmp + (int)rank;
-      const int b = tm / per_img;  // >= batch for the odd tail tile: TMA zero-fills, epilogue masks
-      const int r = tm - b * per_img;
-      const int ty = r / p.tiles_x;
-      const int y0 = ty * Cfg::TH, x0 = (r - ty * p.tiles_x) * Cfg::TW;
+      int tb[MT], ty0[MT], tx0[MT];
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        const int tm = (2 * tmp + (int)rank) * MT + h;
+        tb[h] = tm / per_img;  // >= batch for the tail tiles: TMA zero-fills, epilogue masks
+        const int r = tm - tb[h] * per_img;
+        const int ty = r / p.tiles_x;
+        ty0[h] = ty * Cfg::TH;
+        tx0[h] = (r - ty * p.tiles_x) * Cfg::TW;
+      }
       for (int cb = 0; cb < p.cblocks; ++cb) {
         mbar_wait(AEMPTY(sa), pha ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(AFULL(sa), 2 * Cfg::A_TX_BYTES);
-          tma_load_4d_2sm(sA + sa * Cfg::A_BYTES, &tmA, mapa_shared(AFULL(sa), 0), cb * 64, x0 - 1, y0 - 1, b);
+          if (leader) mbar_expect_tx(AFULL(sa), 2 * MT * Cfg::A_TX_BYTES);
+#pragma unroll
+          for (int h = 0; h < MT; ++h)
+            tma_load_4d_2sm(sA + sa * Cfg::A_STAGE_BYTES + h * Cfg::A_BYTES, &tmA, mapa_shared(AFULL(sa), 0), cb * 64,
+                            tx0[h] - 1, ty0[h] - 1, tb[h]);
         }
         __syncwarp();
         if (++sa == AS) { sa = 0; pha ^= 1u; }
@@ -166,11 +184,11 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
       mbar_wait(TEMPTY_BAR(as), aphase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
       for (int cb = 0; cb < p.cblocks; ++cb) {
         mbar_wait(AFULL(sa), pha);
         tc_fence_after();
-        const uint32_t a_base = sA + sa * Cfg::A_BYTES;
+        const uint32_t a_base = sA + sa * Cfg::A_STAGE_BYTES;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
@@ -180,14 +198,18 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             mbar_wait(BFULL(sb), phb);
             tc_fence_after();
           }
-          // rows of one 8-pixel group are contiguous (8 x 128 B); groups (output rows) are one 16-pixel line apart
-          const uint64_t adesc = make_sw128_desc_bo(a_base + (uint32_t)(dy * Cfg::HALO_W + dx) * 128u, 16, Cfg::HALO_W * 128,
-                                                    bo_mode ? (uint32_t)dx : 0u);
+          // rows of one 8-pixel group are contiguous (8 x 128 B); groups (output rows) are one patch line apart
+          const uint32_t a_tap = a_base + (uint32_t)(dy * Cfg::HALO_W + dx) * 128u;
           const uint64_t bdesc = make_sw128_desc(sB + sb * Cfg::B_BYTES, 16, 1024);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_h16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((cb | tap | k) != 0));
+            for (int h = 0; h < MT; ++h) {  // every pixel tile of this CTA against the same weight tile
+              const uint64_t adesc = make_sw128_desc_bo(a_tap + (uint32_t)(h * Cfg::A_BYTES), 16, Cfg::HALO_W * 128,
+                                                        bo_mode ? (uint32_t)dx : 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_h16_2sm(d_tmem + (uint32_t)(h * BN), adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((cb | tap | k) != 0));
+            }
             if constexpr (!Cfg::RESIDENT_B) umma_commit_2sm_mc(BEMPTY(sb), 3);
             if (tap == 8) umma_commit_2sm_mc(AEMPTY(sa), 3);
             if (tap == 8 && cb == p.cblocks - 1) umma_commit_2sm_mc(TFULL_BAR(as), 3);
@@ -213,21 +235,23 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t aphase = 0;
     for (int pt = pt0; pt < num_pt; pt += pt_stride) {
       const int tmp = pt / p.tiles_n, tn = pt - tmp * p.tiles_n;
-      TileGeom g;
-      g.tm = 2 * tmp + (int)rank;
-      g.cb_img = g.tm / per_img;
-      const int r = g.tm - g.cb_img * per_img;
-      const int ty = r / p.tiles_x;
-      g.y0 = ty * Cfg::TH;
-      g.x0 = (r - ty * p.tiles_x) * Cfg::TW;
-      const bool tile_valid = g.tm < p.tiles_m;
       if constexpr (MODE != GM_CONV_HEAD) epi_fill_bias<HN, MODE>(p, vec, lane, tn * BN + col0);
       mbar_wait(TFULL_BAR(as), aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + col0);
-      if (tile_valid) {
-        if constexpr (MODE == GM_CONV_HEAD) epi_tile_head(p, t_row, lane, q, g);
-        else epi_tile_dispatch<HN, MODE>(p, t_row, stg, vec, lane, q, g, tn * BN + col0);
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {
+        TileGeom g;
+        g.tm = (2 * tmp + (int)rank) * MT + h;
+        g.cb_img = g.tm / per_img;
+        const int r = g.tm - g.cb_img * per_img;
+        const int ty = r / p.tiles_x;
+        g.y0 = ty * Cfg::TH;
+        g.x0 = (r - ty * p.tiles_x) * Cfg::TW;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + h) * BN + col0);
+        if (g.tm < p.tiles_m) {
+          if constexpr (MODE == GM_CONV_HEAD) epi_tile_head(p, t_row, lane, q, g);
+          else epi_tile_dispatch<HN, MODE>(p, t_row, stg, vec, lane, q, g, tn * BN + col0);
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -122,7 +122,7 @@ static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
     DAV2_CUDA_OK(cudaFuncSetAttribute(conv_halo_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     device_setup_mark(&tag);
   }
-  const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  const int pairs = ((p.tiles_m + 2 * Cfg::MT - 1) / (2 * Cfg::MT)) * p.tiles_n;
   if (pairs <= 0) return 0;
   if (Cfg::RESIDENT_B && (p.num_kb > Cfg::B_STAGES || p.tiles_n != 1)) {
     set_last_error("conv_halo<%d>: %d weight tiles do not fit the resident set (%d)", BN, p.num_kb, Cfg::B_STAGES);

@@ -50,6 +50,15 @@ if what in ("conv", "all"):
         if what == "conv":
             ops.conv3x3_h16(x1, w1, bias, x1, x1, 0, want_relu=True)  # RCU conv2: two skip adds + dual output
         ops.conv3x3_h16(x2, w2, bias2, None, None, 0)   # output_conv1 at 296^2, 256 -> 128
+    if os.environ.get("DAV2_TIME"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for name, fn, fl in (("RCU conv 256->256 @148^2", lambda: ops.conv3x3_h16(x1, w1, bias, None, None, 2), 2.0 * B * 148 * 148 * 256 * 256 * 9),
+                             ("output_conv1 256->128 @296^2", lambda: ops.conv3x3_h16(x2, w2, bias2, None, None, 0), 2.0 * B * 296 * 296 * 256 * 128 * 9)):
+            fn(); torch.cuda.synchronize(); e0.record()
+            for _ in range(10): fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print("%-30s %.3f ms  %.0f TFLOP/s" % (name, ms, fl / ms / 1e9))
 if what == "attn5477":  # BASELINE config 5: 16 frames of 1036^2 -> 5477 tokens per image
     qkv5 = rnd(16 * 5477, 3 * D, scale=float(os.environ.get("DAV2_QKV_SCALE", "1.0")))
     for _ in range(reps):
