@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from . import evaluation, ops, sharding
+from . import ops, sharding
 from .pose_estimation_model import stack_pairs  # noqa: F401  (the windowed form below is the same stacking)
 
 
