@@ -354,7 +354,7 @@ int conv3x3(int mode, const h16* in, int B, int H, int W, int Cin, const h16* Wp
   pick_conv_tile(H, W, &tw, &th);
   const int cblocks = (Cin + 63) / 64;
   const int Kp = 9 * cblocks * 64;
-  // halo-reuse kernel: fixed 8 x 16 output tile, one (16 x 18)-pixel patch per channel block
+  // halo-reuse kernel: fixed 8 x 16 output tile, one (10 x 18)-pixel patch per channel block
   const bool halo = conv_halo_eligible(bn, mode, B * ((W + 7) / 8) * ((H + 15) / 16));
   if (halo) { tw = 8; th = 16; }
   const int tiles_m_all = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
