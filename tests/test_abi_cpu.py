@@ -117,3 +117,24 @@ def test_finalizers_on_host():
     for k in ref2:
         assert abs(got2[k] - ref2[k]) < 1e-6
     assert all(np.isnan(v) for v in cm.finalize_calculate_metrics(np.zeros(8)).values())
+
+
+def test_bench_traffic_is_keyed_to_kernel_sources(tmp_path, monkeypatch):
+    """bench.py reports roofline.traffic only from a launch list taken with the CURRENT kernel sources: the committed
+    json carries the sha256 of csrc/ and a mismatch yields null instead of a stale constant."""
+    import json
+    import bench
+    sha = bench.csrc_sha16()
+    assert len(sha) == 16 and sha == bench.csrc_sha16()
+    committed = json.load(open(os.path.join(bench.ROOT, "profiles", "traffic_r02.json")))
+    assert committed["csrc_sha16"] == sha, "profiles/traffic_r02.json was taken with other kernel sources: re-run scripts/gpu_profile.sh + summarise_profiles.py"
+    val, src = bench.measured_traffic()
+    assert src == "traffic_r02.json" and val == committed["gemm_tcgen05_kernel_bytes_per_launch"] > 1e8
+    assert bench.measured_traffic("backproject_kernel_bytes_per_launch")[0] == committed["backproject_kernel_bytes_per_launch"]
+    # a list from other sources is ignored
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "traffic_r02.json").write_text(json.dumps({**committed, "csrc_sha16": "0" * 16}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "csrc_sha16", lambda: sha)
+    assert bench.measured_traffic() == (None, None)
